@@ -1,0 +1,126 @@
+/*
+ * sgfhe_cuda.h -- C ABI of libsgfhe_cuda.so, the B200 (sm_100a) backend for the bootstrapping hot
+ * path of nucypher/SGFHE.jl (Gao's scheme, src/fhe.jl).
+ *
+ * The reference has no FFI; the seam is the call
+ *     bootstrap(bkey::BootstrapKey, rng, enc_bit1::EncryptedBit, enc_bit2::EncryptedBit)
+ * (reference src/fhe.jl:608-621), with external_product (src/fhe.jl:519-530), flatten_poly
+ * (src/utils.jl:253-264) and DarkIntegers' `Polynomial *` (called at src/fhe.jl:527-528) as inner
+ * test seams.  A Julia maintainer binds these with `ccall((:sgfhe_..., "libsgfhe_cuda"), ...)`;
+ * see INTEGRATION.md for the shim.
+ *
+ * Conventions:
+ *  - every value crossing the boundary is a canonical residue (`value(x)` in the reference, never
+ *    the raw Montgomery word), little-endian unsigned;
+ *  - elements of Z_Q are two uint64 (lo, hi) regardless of n ("wide");
+ *  - elements of Z_r (LWE ciphertexts, the type of EncryptedBit.lwe, src/fhe.jl:206-209,272-274)
+ *    are one uint64; an LWE is n+1 values: a[0..n-1] then b;
+ *  - the caller owns every host buffer; the library owns device memory behind the context;
+ *  - every entry point returns 0 on success, a negative sgfhe_status otherwise, never aborts;
+ *    sgfhe_last_error() returns the message of the calling thread's last failure;
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SGFHE_CUDA_H
+#define SGFHE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgfhe_ctx sgfhe_ctx;
+
+enum sgfhe_status {
+  SGFHE_OK = 0,
+  SGFHE_ERR_ARG = -1,      /* mirrors the reference's @assert failures (src/fhe.jl:45-47,238,313) */
+  SGFHE_ERR_MODULUS = -2,  /* mirrors error("Cound not find a modulus") (src/utils.jl:26) / "n is too large" (src/fhe.jl:77) */
+  SGFHE_ERR_CUDA = -3,     /* CUDA runtime failure or no device */
+  SGFHE_ERR_STATE = -4,    /* e.g. bootstrap before a key upload */
+  SGFHE_ERR_NOMEM = -5
+};
+
+/* Scheme parameters, derived exactly as Params(n) does (src/fhe.jl:43-97, src/utils.jl:7-28). */
+typedef struct {
+  int32_t n;            /* polynomial length                         fhe.jl:30    */
+  int32_t t;            /* log2(r) - 1                               fhe.jl:61    */
+  int32_t m;            /* r / 2                                     fhe.jl:62    */
+  int32_t rns_primes;   /* backend detail: 30-bit NTT primes used for the exact convolution */
+  uint64_t r;           /* 16 n                                      fhe.jl:53    */
+  uint64_t q;           /* fhe.jl:57 */
+  uint64_t Dr, Dq;      /* fhe.jl:88-89 */
+  uint64_t Q[2];        /* fhe.jl:64-69 */
+  uint64_t B[2];        /* fhe.jl:87 */
+  uint64_t DQ_tilde[2]; /* fhe.jl:90 */
+} sgfhe_params;
+
+/* Params(n) + device context.  n: power of two, 64 <= n <= 1024 (the reference accepts larger n;
+ * this backend's on-chip NTT is sized for m = 8n <= 8192).  device: CUDA ordinal.
+ * Replaces: Params(n; ...) src/fhe.jl:43. */
+int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out);
+int sgfhe_ctx_destroy(sgfhe_ctx* ctx);
+int sgfhe_params_get(const sgfhe_ctx* ctx, sgfhe_params* out);
+
+/* Params(n) without a device (host arithmetic only; usable on a CPU-only box). */
+int sgfhe_params_derive(int32_t n, sgfhe_params* out);
+
+const char* sgfhe_last_error(void);
+
+/* Upload BootstrapKey.key (src/fhe.jl:176-201) and pre-transform it once into the NTT domain.
+ * key: host, C order [rows][4][2][m][2] uint64 = value(bkey.key[i][j,c].coeffs[k]) (lo,hi),
+ * i = step, j = gadget row (a-digit0, a-digit1, b-digit0, b-digit1), c = column.
+ * rows == n for a usable key; rows < n is accepted for truncated traces only. */
+int sgfhe_bkey_upload(sgfhe_ctx* ctx, const uint64_t* key, int32_t rows);
+
+/* bootstrap(bkey, rng|nothing, enc_bit1, enc_bit2) for a batch of independent gates
+ * (src/fhe.jl:608-621 -> _bootstrap_internal src/fhe.jl:559-595 -> reduce_modulus src/fhe.jl:644-648).
+ * lwe1, lwe2: host [batch][n+1] over Z_r.  out_*: host [batch][n+1] over Z_r.
+ * draws: NULL selects flatten(rng::Nothing, ...) (src/utils.jl:155-189).  Otherwise host int64
+ * [batch][n][2][m][2]: the values rand(rng, -xmax:xmax) the caller's RNG yields in the reference's
+ * order -- step k, polynomial a then b, coefficient, digit (src/fhe.jl:524-525, src/utils.jl:228-230,
+ * 257-258). */
+int sgfhe_bootstrap_batch(sgfhe_ctx* ctx, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,
+                          const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor);
+
+/* Same, all six buffers already in device memory of ctx's device (draws may be NULL).
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+int sgfhe_bootstrap_batch_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* d_lwe1,
+                                 const uint64_t* d_lwe2, const int64_t* d_draws, uint64_t* d_out_and,
+                                 uint64_t* d_out_or, uint64_t* d_out_xor, void* stream);
+
+/* _bootstrap_internal for one gate with the accumulator after every step
+ * (src/fhe.jl:559-595; loop body src/fhe.jl:579-582).  n_steps <= uploaded rows.
+ * draws: NULL or [n_steps][2][m][2].  trace: NULL or [n_steps][2][m][2] uint64 (a then b, wide).
+ * out_*: [n+1][2] wide, over Z_Q, i.e. before reduce_modulus. */
+int sgfhe_bootstrap_trace(sgfhe_ctx* ctx, const uint64_t* lwe1, const uint64_t* lwe2, const int64_t* draws,
+                          int32_t n_steps, uint64_t* trace, uint64_t* out_and, uint64_t* out_or,
+                          uint64_t* out_xor);
+
+/* Negacyclic products in Z_Q[x]/(x^m+1): out[i] = a[i] * b[i], DarkIntegers `Polynomial *` as called at
+ * src/fhe.jl:195,527-528.  a, b, out: host [batch][m][2] wide canonical. */
+int sgfhe_polymul(sgfhe_ctx* ctx, int32_t batch, const uint64_t* a, const uint64_t* b, uint64_t* out);
+/* Same with device buffers, asynchronous on `stream`. */
+int sgfhe_polymul_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* d_a, const uint64_t* d_b,
+                         uint64_t* d_out, void* stream);
+
+/* flatten_poly(rng|nothing, a, Val(B), Val(2)) (src/utils.jl:253-264): a host [m][2] wide;
+ * draws NULL or [m][2]; out [2][m][2] wide (digit polynomials as residues mod Q). */
+int sgfhe_flatten_poly(sgfhe_ctx* ctx, const uint64_t* a, const int64_t* draws, uint64_t* out);
+
+/* external_product(rng|nothing, a, b, A, Val(B), Val(2)) (src/fhe.jl:519-530): a, b [m][2] wide,
+ * A [4][2][m][2] wide coefficient form, draws NULL or [2][m][2]; a_out, b_out [m][2] wide. */
+int sgfhe_external_product(sgfhe_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* A,
+                           const int64_t* draws, uint64_t* a_out, uint64_t* b_out);
+
+/* Kernel launches issued by this library in the calling process since load (for bench accounting). */
+uint64_t sgfhe_launch_count(void);
+
+/* Device pointer / size of the pre-transformed key (NCCL broadcast between ranks, src: none --
+ * the reference is single-process).  After a broadcast into this buffer call sgfhe_bkey_adopt. */
+int sgfhe_bkey_device_buffer(sgfhe_ctx* ctx, int32_t rows, void** d_ptr, uint64_t* bytes);
+int sgfhe_bkey_adopt(sgfhe_ctx* ctx, int32_t rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,76 @@
+"""Loader for libsgfhe_cuda.so (the C ABI declared in include/sgfhe_cuda.h).
+
+The library is built in-tree by `build()` (nvcc, sm_100a only).  There is no CPU fallback: if the
+library is missing or no CUDA device is present, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libsgfhe_cuda.so")
+_LIB = None
+
+# every symbol include/sgfhe_cuda.h declares
+SYMBOLS = [
+    "sgfhe_ctx_create", "sgfhe_ctx_destroy", "sgfhe_params_get", "sgfhe_params_derive", "sgfhe_last_error",
+    "sgfhe_bkey_upload", "sgfhe_bootstrap_batch", "sgfhe_bootstrap_batch_device", "sgfhe_bootstrap_trace",
+    "sgfhe_polymul", "sgfhe_polymul_device", "sgfhe_flatten_poly", "sgfhe_external_product",
+    "sgfhe_launch_count", "sgfhe_bkey_device_buffer", "sgfhe_bkey_adopt",
+]
+
+
+class ParamsC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("t", C.c_int32), ("m", C.c_int32), ("rns_primes", C.c_int32),
+                ("r", C.c_uint64), ("q", C.c_uint64), ("Dr", C.c_uint64), ("Dq", C.c_uint64),
+                ("Q", C.c_uint64 * 2), ("B", C.c_uint64 * 2), ("DQ_tilde", C.c_uint64 * 2)]
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in ("sgfhe_cuda.cu", "device_math.cuh", "host_math.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "sgfhe_cuda.h"))
+    stale = (not os.path.exists(SO_PATH)) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", src_dir, "-s"] + (["-B"] if force else []))
+    return SO_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f"{SO_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        vp, i32, u64p = C.c_void_p, C.c_int32, C.c_void_p
+        L.sgfhe_last_error.restype = C.c_char_p
+        L.sgfhe_launch_count.restype = C.c_uint64
+        L.sgfhe_ctx_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.sgfhe_ctx_destroy.argtypes = [vp]
+        L.sgfhe_params_get.argtypes = [vp, C.POINTER(ParamsC)]
+        L.sgfhe_params_derive.argtypes = [i32, C.POINTER(ParamsC)]
+        L.sgfhe_bkey_upload.argtypes = [vp, u64p, i32]
+        L.sgfhe_bootstrap_batch.argtypes = [vp, i32, u64p, u64p, vp, u64p, u64p, u64p]
+        L.sgfhe_bootstrap_batch_device.argtypes = [vp, i32, u64p, u64p, vp, u64p, u64p, u64p, vp]
+        L.sgfhe_bootstrap_trace.argtypes = [vp, u64p, u64p, vp, i32, u64p, u64p, u64p, u64p]
+        L.sgfhe_polymul.argtypes = [vp, i32, u64p, u64p, u64p]
+        L.sgfhe_polymul_device.argtypes = [vp, i32, u64p, u64p, u64p, vp]
+        L.sgfhe_flatten_poly.argtypes = [vp, u64p, vp, u64p]
+        L.sgfhe_external_product.argtypes = [vp, u64p, u64p, u64p, vp, u64p, u64p]
+        L.sgfhe_bkey_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_uint64)]
+        L.sgfhe_bkey_adopt.argtypes = [vp, i32]
+        _LIB = L
+    return _LIB
+
+
+class SgfheError(RuntimeError):
+    """Raised where the reference would throw (AssertionError / ErrorException)."""
+
+
+def check(rc: int):
+    if rc != 0:
+        raise SgfheError(f"libsgfhe_cuda status {rc}: {lib().sgfhe_last_error().decode()}")

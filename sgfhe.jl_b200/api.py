@@ -1,0 +1,322 @@
+"""Host-side mirror of SGFHE.jl's public API for the bootstrapping path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (exports: src/SGFHE.jl:10-20):
+Params, PrivateKey, BootstrapKey, encrypt, decrypt, split_ciphertext, bootstrap.  The reference's
+`rng::AbstractRNG` is a `numpy.random.Generator` here and `nothing` is `None`.  Everything that is
+arithmetic on the hot path (polynomial products, flatten, the accumulation loop, extract, ModRed)
+runs in libsgfhe_cuda.so; this module only prepares inputs in the reference's formats.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SgfheError, check
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _wide_to_int(w) -> int:
+    return int(w[0]) | (int(w[1]) << 64)
+
+
+class Params:
+    """Params(n) -- src/fhe.jl:27-99.  Raises SgfheError where the reference asserts/errors."""
+
+    def __init__(self, n: int, device: int = 0):
+        pc = _lib.ParamsC()
+        check(_lib.lib().sgfhe_params_derive(int(n), C.byref(pc)))
+        self.n, self.t, self.m = pc.n, pc.t, pc.m
+        self.r, self.q, self.Dr, self.Dq = pc.r, pc.q, pc.Dr, pc.Dq
+        self.Q, self.B, self.DQ_tilde = _wide_to_int(pc.Q), _wide_to_int(pc.B), _wide_to_int(pc.DQ_tilde)
+        self.device = device
+        self._ctx = None
+
+    @property
+    def ctx(self):
+        """Device context (created on first use; fails loudly without a GPU)."""
+        if self._ctx is None:
+            h = C.c_void_p()
+            check(_lib.lib().sgfhe_ctx_create(self.n, self.device, C.byref(h)))
+            self._ctx = h
+        return self._ctx
+
+    def close(self):
+        if self._ctx is not None:
+            _lib.lib().sgfhe_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PrivateKey:
+    """PrivateKey(params, rng) -- src/fhe.jl:130-138: n random bits."""
+
+    def __init__(self, params: Params, rng: np.random.Generator):
+        self.params = params
+        self.key = rng.integers(0, 2, size=params.n, dtype=np.uint8)
+
+
+class LWE:
+    """src/fhe.jl:206-223.  a: uint64[n], b: int, both over Z_r."""
+
+    def __init__(self, a, b):
+        self.a = np.asarray(a, dtype=np.uint64)
+        self.b = int(b)
+
+    def flat(self) -> np.ndarray:
+        return np.concatenate([self.a, np.array([self.b], np.uint64)])
+
+    def __eq__(self, other):
+        return np.array_equal(self.a, other.a) and self.b == other.b
+
+
+class EncryptedBit:
+    """src/fhe.jl:272-278"""
+
+    def __init__(self, lwe: LWE):
+        self.lwe = lwe
+
+    def __eq__(self, other):
+        return self.lwe == other.lwe
+
+
+class PackedCiphertext:
+    """src/fhe.jl:251-254: RLWE (a, b) over (x^n+1, r)."""
+
+    def __init__(self, params: Params, a, b):
+        self.params = params
+        self.a = np.asarray(a, np.uint64)
+        self.b = np.asarray(b, np.uint64)
+
+
+def _negacyclic_small(a: np.ndarray, s: np.ndarray, modulus: int) -> np.ndarray:
+    """a * s in Z_modulus[x]/(x^n+1) for a binary s (host; length-n ciphertext work, not the hot path)."""
+    n = a.shape[0]
+    full = np.convolve(a.astype(np.int64), s.astype(np.int64))
+    res = full[:n].copy()
+    res[: n - 1] -= full[n:]
+    return np.mod(res, modulus).astype(np.uint64)
+
+
+def encrypt(key: PrivateKey, rng: np.random.Generator, message) -> PackedCiphertext:
+    """encrypt(key::PrivateKey, rng, message) -- src/fhe.jl:369-372 -> _encrypt_private src/fhe.jl:310-328.
+
+    `a` is drawn from rng directly: the reference expands a random seed with a MersenneTwister
+    (deterministic_expand, src/utils.jl:63-68, marked TODO upstream); any uniform a over Z_r is a valid ciphertext."""
+    P = key.params
+    message = np.asarray(message, dtype=np.uint8)
+    if message.shape != (P.n,):
+        raise SgfheError("message must have length n (src/fhe.jl:313)")
+    a = rng.integers(0, P.r, size=P.n, dtype=np.uint64)
+    wr = P.Dr // 8
+    w = rng.integers(-wr, wr + 1, size=P.n, dtype=np.int64)                       # src/fhe.jl:318-319
+    b = (_negacyclic_small(a, key.key, P.r).astype(np.int64) + w + message.astype(np.int64) * P.Dr) % P.r   # :322
+    step = 1 << (P.t - 4)
+    b = (b // step) * step                                                         # src/fhe.jl:325
+    return PackedCiphertext(P, a, b.astype(np.uint64))
+
+
+def _extract_r(a: np.ndarray, i: int, n: int, r: int) -> np.ndarray:
+    """extract(a, i, n) over Z_r -- src/fhe.jl:237-244 (i is 1-based)."""
+    N = a.shape[0]
+    if i < n:
+        tail = a[N - (n - i):][::-1]
+        return np.concatenate([a[:i][::-1], np.where(tail == 0, 0, r - tail).astype(np.uint64)])
+    return a[i - n:i][::-1].copy()
+
+
+def split_ciphertext(ct: PackedCiphertext) -> list[EncryptedBit]:
+    """src/fhe.jl:287-290"""
+    P = ct.params
+    return [EncryptedBit(LWE(_extract_r(ct.a, i, P.n, P.r), ct.b[i - 1])) for i in range(1, P.n + 1)]
+
+
+def decrypt(key: PrivateKey, ct):
+    """decrypt(key, ::EncryptedBit) src/fhe.jl:504-507; decrypt(key, ::PackedCiphertext) src/fhe.jl:471-494."""
+    P = key.params
+    if isinstance(ct, EncryptedBit):
+        b1 = (ct.lwe.b - int(ct.lwe.a[key.key.astype(bool)].sum())) % P.r
+        v = ((b1 + P.Dr // 2) % P.r) // P.Dr
+        if v > 1:
+            raise SgfheError("InexactError: decrypted value is not a Bool (src/fhe.jl:506)")
+        return bool(v)
+    b1 = (ct.b.astype(np.int64) - _negacyclic_small(ct.a, key.key, P.r).astype(np.int64)) % P.r
+    v = ((b1 + P.Dr // 2) % P.r) // P.Dr
+    if (v > 1).any():
+        raise SgfheError("InexactError: decrypted value is not a Bool (src/fhe.jl:493)")
+    return v.astype(bool)
+
+
+def _wide_add_small(w: np.ndarray, e: np.ndarray, Q: int) -> np.ndarray:
+    """(w + e) mod Q for wide w in [0,Q) (uint64[...,2]) and small signed e (|e| < 2^62)."""
+    lo, hi = w[..., 0], w[..., 1]
+    eu = e.astype(np.int64).view(np.uint64)
+    with np.errstate(over="ignore"):
+        lo2 = lo + eu
+        carry = ((e >= 0) & (lo2 < lo)).astype(np.uint64)
+        borrow = ((e < 0) & (lo2 > lo)).astype(np.uint64)
+        hi2 = hi + carry - borrow
+        qlo, qhi = np.uint64(Q & 0xFFFFFFFFFFFFFFFF), np.uint64(Q >> 64)
+        neg = (hi2 >> np.uint64(63)) != 0                       # went below zero: add Q
+        ge = ~neg & ((hi2 > qhi) | ((hi2 == qhi) & (lo2 >= qlo)))   # >= Q: subtract Q
+        lo3 = np.where(neg, lo2 + qlo, np.where(ge, lo2 - qlo, lo2))
+        c_add = (neg & (lo3 < lo2)).astype(np.uint64)
+        b_sub = (ge & (lo2 < qlo)).astype(np.uint64)
+        hi3 = np.where(neg, hi2 + qhi + c_add, np.where(ge, hi2 - qhi - b_sub, hi2))
+    return np.stack([lo3, hi3], axis=-1)
+
+
+def _rand_below(rng: np.random.Generator, bound: int, shape) -> np.ndarray:
+    """uniform on [0, bound) as wide uint64[..., 2] (rejection sampling)"""
+    bits = bound.bit_length()
+    n = int(np.prod(shape))
+    out = np.zeros((n, 2), np.uint64)
+    todo = np.arange(n)
+    lo_mask = np.uint64((1 << min(bits, 64)) - 1)
+    hi_mask = np.uint64((1 << max(bits - 64, 0)) - 1)
+    bh, bl = np.uint64(bound >> 64), np.uint64(bound & 0xFFFFFFFFFFFFFFFF)
+    while todo.size:
+        lo = rng.integers(0, 1 << 64, size=todo.size, dtype=np.uint64) & lo_mask
+        hi = rng.integers(0, 1 << 64, size=todo.size, dtype=np.uint64) & hi_mask
+        ok = (hi < bh) | ((hi == bh) & (lo < bl))
+        out[todo[ok], 0] = lo[ok]
+        out[todo[ok], 1] = hi[ok]
+        todo = todo[~ok]
+    return out.reshape(tuple(shape) + (2,))
+
+
+class BootstrapKey:
+    """BootstrapKey(rng, sk) -- src/fhe.jl:176-203.
+
+    Per row i the draws are a_1..a_4 (uniform on [0,Q), m each) then e_1..e_4 (uniform on [-n,n]) as at
+    src/fhe.jl:193-194; the 4n products a_j * ext_key (src/fhe.jl:195) run on the GPU through
+    sgfhe_polymul.  `key` (uint64[n,4,2,m,2], canonical wide residues) is kept on the host in the
+    reference's layout and uploaded/pre-transformed once."""
+
+    def __init__(self, rng: np.random.Generator | None = None, sk: PrivateKey | None = None, *,
+                 params: Params | None = None, key: np.ndarray | None = None, rows: int | None = None):
+        if key is not None:                       # adopt an existing key[i][j,c] array
+            self.params = params
+            self.key = np.ascontiguousarray(key, np.uint64)
+        else:
+            P = sk.params
+            self.params = P
+            ext = np.zeros((P.m, 2), np.uint64)
+            ext[: P.n, 0] = sk.key                                                   # src/fhe.jl:185
+            nrows = P.n if rows is None else rows
+            self.key = np.zeros((nrows, 4, 2, P.m, 2), np.uint64)
+            chunk = max(1, min(nrows, (1 << 22) // (4 * P.m)))
+            for i0 in range(0, nrows, chunk):
+                i1 = min(nrows, i0 + chunk)
+                aj = np.zeros((i1 - i0, 4, P.m, 2), np.uint64)
+                ej = np.zeros((i1 - i0, 4, P.m), np.int64)
+                for i in range(i0, i1):
+                    aj[i - i0] = _rand_below(rng, P.Q, (4, P.m))                     # src/fhe.jl:193
+                    ej[i - i0] = rng.integers(-P.n, P.n + 1, size=(4, P.m), dtype=np.int64)   # src/fhe.jl:194
+                prod = polymul(P, aj.reshape(-1, P.m, 2), np.broadcast_to(ext, ((i1 - i0) * 4, P.m, 2)))
+                bj = _wide_add_small(prod.reshape(i1 - i0, 4, P.m, 2), ej, P.Q)       # src/fhe.jl:195
+                self.key[i0:i1, :, 0] = aj
+                self.key[i0:i1, :, 1] = bj
+                for i in range(i0, i1):                                              # + s_i G  src/fhe.jl:196, 119-122
+                    if sk.key[i]:
+                        g = np.array([1, P.B, 1, P.B], dtype=object)
+                        for j in range(4):
+                            c = 0 if j < 2 else 1
+                            cell = self.key[i, j, c, 0]
+                            v = (_wide_to_int(cell) + int(g[j])) % P.Q
+                            cell[0], cell[1] = v & 0xFFFFFFFFFFFFFFFF, v >> 64
+        self._uploaded = False
+
+    def upload(self):
+        if not self._uploaded:
+            check(_lib.lib().sgfhe_bkey_upload(self.params.ctx, _ptr(self.key), self.key.shape[0]))
+            self._uploaded = True
+
+
+def _draws(P: Params, rng: np.random.Generator, shape) -> np.ndarray:
+    """rand(rng, -xmax:xmax) with xmax = 3 (B / 2) -- src/utils.jl:210-216, 229"""
+    xmax = (P.B // 2) * 3
+    return rng.integers(-xmax, xmax + 1, size=shape, dtype=np.int64)
+
+
+def bootstrap_batch(bkey: BootstrapKey, rng, lwes1: np.ndarray, lwes2: np.ndarray):
+    """Batched form of `bootstrap`: lwes1, lwes2 uint64[batch, n+1] -> (and, or, xor) uint64[batch, n+1]."""
+    P = bkey.params
+    lwes1 = np.ascontiguousarray(lwes1, np.uint64)
+    lwes2 = np.ascontiguousarray(lwes2, np.uint64)
+    if lwes1.shape != lwes2.shape or lwes1.ndim != 2 or lwes1.shape[1] != P.n + 1:
+        raise SgfheError("LWE arrays must be [batch, n+1]")
+    bkey.upload()
+    batch = lwes1.shape[0]
+    draws = None if rng is None else _draws(P, rng, (batch, P.n, 2, P.m, 2))   # order: src/fhe.jl:524-525, utils.jl:257-258
+    outs = [np.zeros_like(lwes1) for _ in range(3)]
+    check(_lib.lib().sgfhe_bootstrap_batch(P.ctx, batch, _ptr(lwes1), _ptr(lwes2), _ptr(draws), *[_ptr(o) for o in outs]))
+    return tuple(outs)
+
+
+def bootstrap(bkey: BootstrapKey, rng, enc_bit1: EncryptedBit, enc_bit2: EncryptedBit):
+    """bootstrap(bkey, rng|nothing, enc_bit1, enc_bit2) -> (AND, OR, XOR) -- src/fhe.jl:608-621."""
+    outs = bootstrap_batch(bkey, rng, enc_bit1.lwe.flat()[None, :], enc_bit2.lwe.flat()[None, :])
+    return tuple(EncryptedBit(LWE(o[0, :-1], o[0, -1])) for o in outs)
+
+
+# ---- inner seams (test/internals.test.jl level) ---------------------------------------------------------
+def polymul(P: Params, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """DarkIntegers `Polynomial *` in Z_Q[x]/(x^m+1), batched: wide uint64[batch, m, 2]."""
+    a = np.ascontiguousarray(a, np.uint64)
+    b = np.ascontiguousarray(b, np.uint64)
+    single = a.ndim == 2
+    if single:
+        a, b = a[None], b[None]
+    if a.shape != b.shape or a.shape[1:] != (P.m, 2):
+        raise SgfheError("operands must be [batch, m, 2]")
+    out = np.zeros_like(a)
+    check(_lib.lib().sgfhe_polymul(P.ctx, a.shape[0], _ptr(a), _ptr(b), _ptr(out)))
+    return out[0] if single else out
+
+
+def flatten_poly(P: Params, rng_draws, a: np.ndarray) -> np.ndarray:
+    """flatten_poly(rng|nothing, a, Val(B), Val(2)) -- src/utils.jl:253-264.  rng_draws: None or int64[m,2]."""
+    a = np.ascontiguousarray(a, np.uint64)
+    d = None if rng_draws is None else np.ascontiguousarray(rng_draws, np.int64)
+    out = np.zeros((2, P.m, 2), np.uint64)
+    check(_lib.lib().sgfhe_flatten_poly(P.ctx, _ptr(a), _ptr(d), _ptr(out)))
+    return out
+
+
+def external_product(P: Params, rng_draws, a, b, A):
+    """external_product(rng|nothing, a, b, A, Val(B), Val(2)) -- src/fhe.jl:519-530.  A: wide [4,2,m,2]."""
+    a = np.ascontiguousarray(a, np.uint64)
+    b = np.ascontiguousarray(b, np.uint64)
+    A = np.ascontiguousarray(A, np.uint64)
+    d = None if rng_draws is None else np.ascontiguousarray(rng_draws, np.int64)
+    oa, ob = np.zeros_like(a), np.zeros_like(b)
+    check(_lib.lib().sgfhe_external_product(P.ctx, _ptr(a), _ptr(b), _ptr(A), _ptr(d), _ptr(oa), _ptr(ob)))
+    return oa, ob
+
+
+def bootstrap_trace(bkey: BootstrapKey, draws, lwe1, lwe2, n_steps: int | None = None, trace: bool = True):
+    """_bootstrap_internal (src/fhe.jl:559-595) for one gate: outputs over Z_Q plus the accumulator after each step."""
+    P = bkey.params
+    bkey.upload()
+    n_steps = bkey.key.shape[0] if n_steps is None else n_steps
+    lwe1 = np.ascontiguousarray(lwe1, np.uint64)
+    lwe2 = np.ascontiguousarray(lwe2, np.uint64)
+    d = None if draws is None else np.ascontiguousarray(draws, np.int64)
+    tr = np.zeros((n_steps, 2, P.m, 2), np.uint64) if trace else None
+    outs = [np.zeros((P.n + 1, 2), np.uint64) for _ in range(3)]
+    check(_lib.lib().sgfhe_bootstrap_trace(P.ctx, _ptr(lwe1), _ptr(lwe2), _ptr(d), n_steps, _ptr(tr), *[_ptr(o) for o in outs]))
+    return outs[0], outs[1], outs[2], tr
+
+
+def launch_count() -> int:
+    return int(_lib.lib().sgfhe_launch_count())

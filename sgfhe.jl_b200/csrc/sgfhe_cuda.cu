@@ -1,0 +1,710 @@
+// sgfhe_cuda.cu -- kernels and C ABI of libsgfhe_cuda.so (see include/sgfhe_cuda.h).
+//
+// Hot path = reference src/fhe.jl:559-595 (_bootstrap_internal) + src/fhe.jl:608-621 (bootstrap), in the
+// algebraically identical form  (a,b) += (x^u - 1) * ([flatten(a); flatten(b)] . C^(k))  with the key C
+// pre-transformed once.  One persistent CTA owns one gate for all n steps; only
+// pre-transformed key tiles stream in (from L2: every resident CTA is on a nearby step).
+#include "../../include/sgfhe_cuda.h"
+#include "device_math.cuh"
+#include "host_math.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sgfhe;
+
+// =========================================================================================================
+// Kernels
+// =========================================================================================================
+
+enum : int { F_INIT = 1, F_FINAL = 2, F_RAW = 4, F_EXT = 8 };
+
+struct GateArgs {
+  const uint64_t* lwe1; const uint64_t* lwe2;   // [batch][n+1] over Z_r
+  const int64_t* draws;                         // NULL or [batch][draw_steps][2][m][2]
+  uint64_t* out_and; uint64_t* out_or; uint64_t* out_xor;   // [batch][n+1] (Z_r) or wide [batch][n+1][2] with F_RAW
+  uint64_t* trace;                              // NULL or [2][m][2]: accumulator after the last step run
+  const uint32_t* keyhat;                       // [rows][L][4][2][m] Montgomery form, NTT order
+  const uint2* tw_f; const uint2* tw_i;         // [MAXP][m]
+  uint8_t* scratch; size_t scratch_stride;      // per CTA
+  int batch, step_begin, step_end, draw_steps, flags;
+};
+
+struct Scratch { uint32_t* acc; int64_t* dig; uint32_t* zq; uint32_t* zres; };
+__device__ __forceinline__ Scratch carve(uint8_t* base, int m) {
+  Scratch s;
+  s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
+  s.dig = reinterpret_cast<int64_t*>(base + (size_t)24 * m);          // [4][m]
+  s.zq = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);          // [2][3][m], aliases dig
+  s.zres = reinterpret_cast<uint32_t*>(base + (size_t)56 * m);        // [L][2][m]
+  return s;
+}
+static size_t scratch_bytes(int m, int L) { return (size_t)(56 + 8 * L) * m; }
+
+// accumulator init: a = 0, b = t(x) x^(-u_b) DQ   (src/fhe.jl:566-573, t(x) from src/fhe.jl:535-548)
+__device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
+  const int m = C.m;
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const int src = (int)((j + ub) & (uint64_t)(2 * m - 1));
+    const int idx = src & (m - 1);
+    int sgn = idx < m / 2 ? 1 : (idx == m / 2 ? 0 : -1);     // Dr = m/2: +1 on [0,m/2), 0, -1 on (m/2,m)
+    if (src >= m) sgn = -sgn;
+    const u128 v = sgn == 0 ? (u128)0 : (sgn > 0 ? C.DQ : C.Q - C.DQ);
+    store3(S.acc, m, j, 0);
+    store3(S.acc + 3 * m, m, j, v);
+  }
+}
+
+// One accumulation step (body of src/fhe.jl:579-582).  u = rotation amount in [0, 2m).
+__device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
+                          const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
+                          const int64_t* __restrict__ draws, int u, bool ext) {
+  const int m = C.m, nthr = blockDim.x, tid = threadIdx.x;
+  // Phase A: gadget decomposition of both accumulator polynomials (src/utils.jl:253-264; a then b)
+  for (int idx = tid; idx < m; idx += nthr) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const u128 v = load3(S.acc + c * 3 * m, m, idx);
+      int64_t x0 = 0, x1 = 0, d0, d1;
+      if (draws) { x0 = draws[((size_t)c * m + idx) * 2]; x1 = draws[((size_t)c * m + idx) * 2 + 1]; }
+      decompose(C, v, x0, x1, draws != nullptr, d0, d1);
+      S.dig[(2 * c) * m + idx] = d0;
+      S.dig[(2 * c + 1) * m + idx] = d1;
+    }
+  }
+  __syncthreads();
+  // Phase B: per RNS prime -- 4 forward NTTs, 8 MACs against the key tile, 2 inverse NTTs
+  for (int i = 0; i < C.L; ++i) {
+    const uint32_t p = C.p[i];
+    for (int e = tid; e < 4 * m; e += nthr) {
+      const int j = e >> C.logm, idx = e & (m - 1);
+      sm[j * m + swz(idx)] = digit_mod(C, i, S.dig[e]);
+    }
+    __syncthreads();
+    ntt_forward(sm, 4, m, C.logm, tw_f + (size_t)i * m, p);
+    const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
+    for (int idx = tid; idx < m; idx += nthr) {
+      uint64_t sa = 0, sb = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t d = sm[j * m + swz(idx)];
+        d = min(d, d - 2 * p); d = min(d, d - p);
+        sa += (uint64_t)d * __ldg(&K[(2 * j) * m + idx]);
+        sb += (uint64_t)d * __ldg(&K[(2 * j + 1) * m + idx]);
+      }
+      sm[swz(idx)] = redc(sa, p, C.pinv_neg[i]);
+      sm[m + swz(idx)] = redc(sb, p, C.pinv_neg[i]);
+    }
+    __syncthreads();
+    ntt_inverse(sm, 2, m, C.logm, tw_i + (size_t)i * m, p);
+    for (int e = tid; e < 2 * m; e += nthr) {
+      const int c = e >> C.logm, idx = e & (m - 1);
+      const uint32_t y = shoup_mul(sm[c * m + swz(idx)], C.scale[0][i], C.scale_sh[0][i], p);
+      S.zres[((size_t)i * 2 + c) * m + idx] = csub(y, p);
+    }
+    __syncthreads();
+  }
+  // Phase C: CRT lift to Z_Q
+  for (int e = tid; e < 2 * m; e += nthr) {
+    const int c = e >> C.logm, idx = e & (m - 1);
+    const u128 z = crt_lift<0>(C, C.L, S.zres + (size_t)c * m + idx, (size_t)2 * m);
+    store3(S.zq + c * 3 * m, m, idx, z);
+  }
+  __syncthreads();
+  // Phase D: acc += x^u z - z   (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product)
+  for (int e = tid; e < 2 * m; e += nthr) {
+    const int c = e >> C.logm, j = e & (m - 1);
+    const u128 z = load3(S.zq + c * 3 * m, m, j);
+    u128 res;
+    if (ext) {
+      res = z;
+    } else {
+      const int src = (j - u) & (2 * m - 1);
+      u128 zr = load3(S.zq + c * 3 * m, m, src & (m - 1));
+      if (src >= m) zr = negmodQ(zr, C.Q);
+      const u128 acc = load3(S.acc + c * 3 * m, m, j);
+      res = addmodQ(acc, submodQ(zr, z, C.Q), C.Q);
+    }
+    store3(S.acc + c * 3 * m, m, j, res);
+  }
+  __syncthreads();
+}
+
+// extract + AND/OR/XOR assembly (src/fhe.jl:585-592) + reduce_modulus (src/fhe.jl:616-618)
+__device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_and, uint64_t* out_or,
+                           uint64_t* out_xor, bool raw) {
+  const int m = C.m, n = C.n;
+  for (int k = threadIdx.x; k <= n; k += blockDim.x) {
+    u128 va, vo;
+    if (k < n) {
+      va = load3(S.acc, m, 3 * m / 4 - k);                           // extract(a, 3m/4+1, n)[k]
+      vo = negmodQ(load3(S.acc, m, m / 4 - k), C.Q);                 // -extract(a, m/4+1, n)[k]
+    } else {
+      va = addmodQ(C.DQ, load3(S.acc + 3 * m, m, 3 * m / 4), C.Q);   // DQ + b[3m/4]
+      vo = submodQ(C.DQ, load3(S.acc + 3 * m, m, m / 4), C.Q);       // DQ - b[m/4]
+    }
+    const u128 vx = submodQ(vo, va, C.Q);                            // a_or - a_and
+    if (raw) {
+      out_and[2 * k] = (uint64_t)va; out_and[2 * k + 1] = (uint64_t)(va >> 64);
+      out_or[2 * k] = (uint64_t)vo; out_or[2 * k + 1] = (uint64_t)(vo >> 64);
+      out_xor[2 * k] = (uint64_t)vx; out_xor[2 * k + 1] = (uint64_t)(vx >> 64);
+    } else {
+      out_and[k] = modred(C, va); out_or[k] = modred(C, vo); out_xor[k] = modred(C, vx);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int m = C.m, n = C.n;
+  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
+  const uint64_t rmask = (1ull << C.logr) - 1;
+  for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
+    const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
+    const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
+    if (A.flags & F_INIT) gate_init(C, S, (l1[n] + l2[n]) & rmask);
+    __syncthreads();
+    for (int k = A.step_begin; k < A.step_end; ++k) {
+      const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
+      const int64_t* dr = A.draws ? A.draws + ((size_t)g * A.draw_steps + (k - A.step_begin)) * 4 * m : nullptr;
+      gate_step(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i, dr, u, (A.flags & F_EXT) != 0);
+    }
+    if (A.trace) {
+      for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
+        const u128 v = load3(S.acc + (e / m) * 3 * m, m, e % m);
+        A.trace[2 * e] = (uint64_t)v; A.trace[2 * e + 1] = (uint64_t)(v >> 64);
+      }
+    }
+    if (A.flags & F_FINAL) {
+      const size_t w = (A.flags & F_RAW) ? 2 : 1;
+      gate_final(C, S, A.out_and + (size_t)g * (n + 1) * w, A.out_or + (size_t)g * (n + 1) * w,
+                 A.out_xor + (size_t)g * (n + 1) * w, (A.flags & F_RAW) != 0);
+    }
+    __syncthreads();
+  }
+}
+
+// Key pre-transform (K10): coefficient-form wide polys -> per-prime NTT domain, Montgomery form.
+// grid = (npolys, L).  coef: [npolys][m][2];  out: poly P of row k=P/8, slot jc=P%8 -> keyhat[((k L + i) 8 + jc) m ..]
+__global__ void __launch_bounds__(1024, 1)
+key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ coef, uint32_t* __restrict__ keyhat,
+                     const uint2* __restrict__ tw_f, int poly0) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int m = C.m, i = blockIdx.y;
+  const uint32_t p = C.p[i];
+  const uint64_t* src = coef + (size_t)blockIdx.x * m * 2;
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+    const u128 c = (u128)src[2 * idx] | ((u128)src[2 * idx + 1] << 64);
+    sm[swz(idx)] = centred_mod(C, i, c);
+  }
+  __syncthreads();
+  ntt_forward(sm, 1, m, C.logm, tw_f + (size_t)i * m, p);
+  const int P = poly0 + blockIdx.x, k = P >> 3, jc = P & 7;
+  uint32_t* dst = keyhat + (((size_t)k * C.L + i) * 8 + jc) * m;
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+    uint32_t v = sm[swz(idx)];
+    v = min(v, v - 2 * p); v = min(v, v - p);
+    dst[idx] = csub(shoup_mul(v, C.mont[i], C.mont_sh[i], p), p);
+  }
+}
+
+// Standalone negacyclic product of two full-size operands (seam for DarkIntegers `Polynomial *`).
+// grid = batch CTAs; scratch per CTA: [LM][m] u32.
+__global__ void __launch_bounds__(1024, 1)
+polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+               uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
+               uint32_t* scratch, int batch) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int m = C.m;
+  uint32_t* zres = scratch + (size_t)blockIdx.x * C.LM * m;
+  for (int g = blockIdx.x; g < batch; g += gridDim.x) {
+    const uint64_t* pa = a + (size_t)g * m * 2; const uint64_t* pb = b + (size_t)g * m * 2;
+    for (int i = 0; i < C.LM; ++i) {
+      const uint32_t p = C.p[i];
+      for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+        sm[swz(idx)] = centred_mod(C, i, (u128)pa[2 * idx] | ((u128)pa[2 * idx + 1] << 64));
+        sm[m + swz(idx)] = centred_mod(C, i, (u128)pb[2 * idx] | ((u128)pb[2 * idx + 1] << 64));
+      }
+      __syncthreads();
+      ntt_forward(sm, 2, m, C.logm, tw_f + (size_t)i * m, p);
+      for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+        uint32_t x = sm[swz(idx)], y = sm[m + swz(idx)];
+        x = min(x, x - 2 * p); x = min(x, x - p); y = min(y, y - 2 * p); y = min(y, y - p);
+        sm[swz(idx)] = redc((uint64_t)x * y, p, C.pinv_neg[i]);
+      }
+      __syncthreads();
+      ntt_inverse(sm, 1, m, C.logm, tw_i + (size_t)i * m, p);
+      for (int idx = threadIdx.x; idx < m; idx += blockDim.x)
+        zres[(size_t)i * m + idx] = csub(shoup_mul(sm[swz(idx)], C.scale[1][i], C.scale_sh[1][i], p), p);
+      __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+      const u128 z = crt_lift<1>(C, C.LM, zres + idx, (size_t)m);
+      out[((size_t)g * m + idx) * 2] = (uint64_t)z; out[((size_t)g * m + idx) * 2 + 1] = (uint64_t)(z >> 64);
+    }
+    __syncthreads();
+  }
+}
+
+// flatten_poly seam (src/utils.jl:253-264): a [m] wide -> out [2][m] wide residues mod Q
+__global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a,
+                               const int64_t* __restrict__ draws, uint64_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C.m) return;
+  const u128 v = (u128)a[2 * idx] | ((u128)a[2 * idx + 1] << 64);
+  int64_t d[2];
+  decompose(C, v, draws ? draws[2 * idx] : 0, draws ? draws[2 * idx + 1] : 0, draws != nullptr, d[0], d[1]);
+  for (int i = 0; i < 2; ++i) {
+    const u128 r = d[i] >= 0 ? (u128)d[i] : C.Q - (u128)(-d[i]);
+    out[((size_t)i * C.m + idx) * 2] = (uint64_t)r; out[((size_t)i * C.m + idx) * 2 + 1] = (uint64_t)(r >> 64);
+  }
+}
+
+// wide [2][m][2] -> accumulator scratch (SoA limbs) and back
+__global__ void acc_load_kernel(int m, const uint64_t* __restrict__ ab, uint32_t* acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * m) return;
+  const u128 v = (u128)ab[2 * e] | ((u128)ab[2 * e + 1] << 64);
+  store3(acc + (e / m) * 3 * m, m, e % m, v);
+}
+
+// =========================================================================================================
+// Host side
+// =========================================================================================================
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct sgfhe_ctx {
+  int device = 0;
+  HostParams hp;
+  DevConst dc;
+  int num_sms = 0, threads = 0, max_ctas = 0;
+  size_t smem_bytes = 0, scratch_stride = 0;
+  uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
+  uint32_t* d_keyhat = nullptr; int key_rows = 0; size_t keyhat_capacity_rows = 0;
+  uint8_t* d_scratch = nullptr; int scratch_ctas = 0;
+  uint32_t* d_pm_scratch = nullptr; int pm_ctas = 0;
+};
+
+static void to_limbs(u128 v, uint32_t out[3]) { out[0] = (uint32_t)v; out[1] = (uint32_t)(v >> 32); out[2] = (uint32_t)(v >> 64); }
+
+static int choose_primes(double need_bits, const std::vector<uint32_t>& primes) {
+  double have = 0;
+  for (size_t k = 0; k < primes.size(); ++k) {
+    have += log2((double)primes[k]);
+    if (have >= need_bits) return (int)k + 1;
+  }
+  return -1;
+}
+
+static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* twf, std::vector<uint2>* twi) {
+  memset(dc, 0, sizeof *dc);
+  const std::vector<uint32_t> primes = h_rns_primes(MAXP);
+  const double lq = log2((double)hp.Q), lB = log2((double)hp.B), lm = hp.logm;
+  // |sum of 4 m products digit * centred key| < 4 m (2B+1) Q/2 ; +1 sign bit, +4 bits for the CRT rounding margin
+  const int L = choose_primes(2 + lm + (lB + 1.001) + (lq - 1) + 1 + 4, primes);
+  const int LM = choose_primes(lm + 2 * (lq - 1) + 1 + 4, primes);
+  if (L < 0 || LM < 0) return -1;
+  dc->n = hp.n; dc->m = hp.m; dc->logm = hp.logm; dc->logr = hp.logr; dc->kB = hp.kB; dc->L = L; dc->LM = LM;
+  dc->sbits = h_bits(hp.Q) - 1;
+  dc->Q = hp.Q; dc->DQ = hp.DQ; dc->B = hp.B;
+  const u128 s = hp.B / 2 - 1;                       // B is even (src/utils.jl:162-166)
+  dc->s = (uint64_t)s;
+  dc->offs = h_mulmod(s, (1 + hp.B) % hp.Q, hp.Q);
+  dc->barrett_mu = (uint64_t)(((u128)1 << (dc->sbits + 35)) / hp.Q);
+  const int NP = L > LM ? L : LM;
+  for (int i = 0; i < NP; ++i) {
+    const uint32_t p = primes[i];
+    dc->p[i] = p;
+    uint32_t inv = p; for (int k = 0; k < 5; ++k) inv *= 2 - p * inv;      // p^-1 mod 2^32
+    dc->pinv_neg[i] = 0u - inv;
+    dc->dig_mu[i] = (uint32_t)(((uint64_t)1 << 50) / p);
+    dc->vinv[i] = (uint32_t)(((uint64_t)1 << 61) / p);
+    dc->r32[i] = (uint32_t)(((uint64_t)1 << 32) % p);
+    dc->r64[i] = (uint32_t)((((u128)1) << 64) % p);
+    dc->qmodp[i] = (uint32_t)(hp.Q % p);
+    dc->mont[i] = dc->r32[i];
+    dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
+    dc->dig_bias[i] = (uint64_t)p * ((((uint64_t)1 << 46) + p - 1) / p);
+  }
+  for (int basis = 0; basis < 2; ++basis) {
+    const int K = basis == 0 ? L : LM;
+    u128 Pm = 1 % hp.Q;
+    for (int i = 0; i < K; ++i) Pm = h_mulmod(Pm, primes[i], hp.Q);
+    to_limbs((hp.Q - Pm) % hp.Q, dc->negP[basis]);
+    for (int i = 0; i < K; ++i) {
+      const uint32_t p = primes[i];
+      u128 c = 1; uint64_t cp = 1;
+      for (int j = 0; j < K; ++j) if (j != i) { c = h_mulmod(c, primes[j], hp.Q); cp = h_mulmod64(cp, primes[j] % p, p); }
+      to_limbs(c, dc->crt_c[basis][i]);
+      uint64_t sc = h_mulmod64(h_powmod64(cp, p - 2, p), h_powmod64((uint64_t)hp.m % p, p - 2, p), p);
+      if (basis == 1) sc = h_mulmod64(sc, dc->r32[i], p);
+      dc->scale[basis][i] = (uint32_t)sc;
+      dc->scale_sh[basis][i] = (uint32_t)((sc << 32) / p);
+    }
+  }
+  const int m = hp.m;
+  twf->assign((size_t)MAXP * m, make_uint2(0, 0)); twi->assign((size_t)MAXP * m, make_uint2(0, 0));
+  std::vector<uint64_t> pf(m), pi(m);
+  for (int i = 0; i < NP; ++i) {
+    const uint64_t p = primes[i];
+    const uint64_t psi = h_root_2m((uint32_t)p, m), psi_inv = h_powmod64(psi, p - 2, p);
+    pf[0] = pi[0] = 1;
+    for (int k = 1; k < m; ++k) { pf[k] = pf[k - 1] * psi % p; pi[k] = pi[k - 1] * psi_inv % p; }
+    for (int k = 0; k < m; ++k) {
+      const int r = h_bitrev(k, hp.logm);
+      (*twf)[(size_t)i * m + k] = make_uint2((uint32_t)pf[r], (uint32_t)((pf[r] << 32) / p));
+      (*twi)[(size_t)i * m + k] = make_uint2((uint32_t)pi[r], (uint32_t)((pi[r] << 32) / p));
+    }
+  }
+  return 0;
+}
+
+extern "C" const char* sgfhe_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t sgfhe_launch_count(void) { return g_launches.load(); }
+
+static void fill_params(const HostParams& hp, int L, sgfhe_params* out) {
+  out->n = hp.n; out->t = hp.t; out->m = hp.m; out->rns_primes = L;
+  out->r = hp.r; out->q = hp.q; out->Dr = hp.Dr; out->Dq = hp.Dq;
+  out->Q[0] = (uint64_t)hp.Q; out->Q[1] = (uint64_t)(hp.Q >> 64);
+  out->B[0] = (uint64_t)hp.B; out->B[1] = (uint64_t)(hp.B >> 64);
+  out->DQ_tilde[0] = (uint64_t)hp.DQ; out->DQ_tilde[1] = (uint64_t)(hp.DQ >> 64);
+}
+
+extern "C" int sgfhe_params_derive(int32_t n, sgfhe_params* out) {
+  if (!out) return fail(SGFHE_ERR_ARG, "out is NULL");
+  HostParams hp;
+  const int rc = h_params(n, &hp);
+  if (rc == -1) return fail(SGFHE_ERR_ARG, "n must be a power of two >= 64 (src/fhe.jl:45-46)");
+  if (rc) return fail(SGFHE_ERR_MODULUS, "could not find a modulus / n is too large (src/utils.jl:26, src/fhe.jl:77)");
+  fill_params(hp, 0, out);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
+  if (!out) return fail(SGFHE_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  HostParams hp;
+  const int rc = h_params(n, &hp);
+  if (rc == -1) return fail(SGFHE_ERR_ARG, "n must be a power of two >= 64 (src/fhe.jl:45-46)");
+  if (rc) return fail(SGFHE_ERR_MODULUS, "could not find a modulus / n is too large (src/utils.jl:26, src/fhe.jl:77)");
+  if (n > 1024) return fail(SGFHE_ERR_ARG, "this backend supports n <= 1024 (m = 8n <= 8192 on-chip NTT)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SGFHE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SGFHE_ERR_ARG, "bad device ordinal");
+  CK(cudaSetDevice(device));
+  sgfhe_ctx* c = new sgfhe_ctx();
+  c->device = device; c->hp = hp;
+  std::vector<uint2> twf, twi;
+  if (build_consts(hp, &c->dc, &twf, &twi)) { delete c; return fail(SGFHE_ERR_MODULUS, "RNS basis too small for these parameters"); }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  const int m = hp.m;
+  c->threads = m / 2 < 128 ? 128 : (m / 2 > 1024 ? 1024 : m / 2);     // 4 polys x m/8 radix-8 blocks
+  c->smem_bytes = (size_t)4 * m * sizeof(uint32_t);
+  CK(cudaFuncSetAttribute(bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  CK(cudaFuncSetAttribute(key_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  CK(cudaFuncSetAttribute(polymul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bootstrap_kernel, c->threads, c->smem_bytes));
+  if (occ < 1) { delete c; return fail(SGFHE_ERR_CUDA, "bootstrap kernel does not fit on an SM"); }
+  c->max_ctas = occ * c->num_sms;
+  c->scratch_stride = (scratch_bytes(m, c->dc.L) + 255) & ~(size_t)255;
+  CK(cudaMalloc(&c->d_tw_f, twf.size() * sizeof(uint2)));
+  CK(cudaMalloc(&c->d_tw_i, twi.size() * sizeof(uint2)));
+  CK(cudaMemcpy(c->d_tw_f, twf.data(), twf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_tw_i, twi.data(), twi.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  *out = c;
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_ctx_destroy(sgfhe_ctx* c) {
+  if (!c) return SGFHE_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch);
+  delete c;
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_params_get(const sgfhe_ctx* c, sgfhe_params* out) {
+  if (!c || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  fill_params(c->hp, c->dc.L, out);
+  return SGFHE_OK;
+}
+
+static size_t keyhat_row_words(const sgfhe_ctx* c) { return (size_t)c->dc.L * 8 * c->hp.m; }
+
+static int ensure_keyhat(sgfhe_ctx* c, int rows) {
+  if ((size_t)rows <= c->keyhat_capacity_rows) return SGFHE_OK;
+  if (c->d_keyhat) { cudaFree(c->d_keyhat); c->d_keyhat = nullptr; c->keyhat_capacity_rows = 0; c->key_rows = 0; }
+  if (cudaMalloc(&c->d_keyhat, (size_t)rows * keyhat_row_words(c) * sizeof(uint32_t)) != cudaSuccess)
+    return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the pre-transformed key failed");
+  c->keyhat_capacity_rows = rows;
+  return SGFHE_OK;
+}
+
+static int ensure_scratch(sgfhe_ctx* c, int ctas) {
+  if (ctas <= c->scratch_ctas) return SGFHE_OK;
+  if (c->d_scratch) { cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_ctas = 0; }
+  if (cudaMalloc(&c->d_scratch, (size_t)ctas * c->scratch_stride) != cudaSuccess)
+    return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the gate scratch failed");
+  c->scratch_ctas = ctas;
+  return SGFHE_OK;
+}
+
+// transform `npolys` coefficient-form polys (host) into keyhat starting at poly index poly0
+static int transform_polys(sgfhe_ctx* c, const uint64_t* h_coef, int poly0, int npolys, uint32_t* d_keyhat) {
+  const int m = c->hp.m;
+  const int chunk = 512;                                   // polys per staging chunk
+  uint64_t* d_stage = nullptr;
+  const size_t poly_bytes = (size_t)m * 2 * sizeof(uint64_t);
+  if (cudaMalloc(&d_stage, (size_t)(npolys < chunk ? npolys : chunk) * poly_bytes) != cudaSuccess)
+    return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the key staging buffer failed");
+  for (int done = 0; done < npolys; done += chunk) {
+    const int cnt = npolys - done < chunk ? npolys - done : chunk;
+    cudaError_t e = cudaMemcpy(d_stage, h_coef + (size_t)done * m * 2, (size_t)cnt * poly_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      key_transform_kernel<<<dim3(cnt, c->dc.L), c->threads, c->smem_bytes>>>(c->dc, d_stage, d_keyhat, c->d_tw_f, poly0 + done);
+      ++g_launches;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(d_stage); return fail(SGFHE_ERR_CUDA, std::string("key transform: ") + cudaGetErrorString(e)); }
+  }
+  cudaFree(d_stage);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_upload(sgfhe_ctx* c, const uint64_t* key, int32_t rows) {
+  if (!c || !key) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (rows < 1 || rows > c->hp.n) return fail(SGFHE_ERR_ARG, "rows must be in [1, n]");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_keyhat(c, rows); if (rc) return rc;
+  rc = transform_polys(c, key, 0, rows * 8, c->d_keyhat); if (rc) return rc;
+  c->key_rows = rows;
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_device_buffer(sgfhe_ctx* c, int32_t rows, void** d_ptr, uint64_t* bytes) {
+  if (!c || !d_ptr || !bytes) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (rows < 1 || rows > c->hp.n) return fail(SGFHE_ERR_ARG, "rows must be in [1, n]");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_keyhat(c, rows); if (rc) return rc;
+  *d_ptr = c->d_keyhat; *bytes = (uint64_t)rows * keyhat_row_words(c) * sizeof(uint32_t);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_adopt(sgfhe_ctx* c, int32_t rows) {
+  if (!c) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (rows < 1 || (size_t)rows > c->keyhat_capacity_rows) return fail(SGFHE_ERR_ARG, "rows exceeds the key buffer");
+  c->key_rows = rows;
+  return SGFHE_OK;
+}
+
+static int launch_gates(sgfhe_ctx* c, GateArgs& A, cudaStream_t st) {
+  const int grid = A.batch < c->max_ctas ? A.batch : c->max_ctas;
+  int rc = ensure_scratch(c, grid); if (rc) return rc;
+  A.keyhat = c->d_keyhat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i;
+  A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
+  bootstrap_kernel<<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const uint64_t* d_lwe1, const uint64_t* d_lwe2,
+                                            const int64_t* d_draws, uint64_t* d_and, uint64_t* d_or, uint64_t* d_xor,
+                                            void* stream) {
+  if (!c || !d_lwe1 || !d_lwe2 || !d_and || !d_or || !d_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  GateArgs A; memset(&A, 0, sizeof A);
+  A.lwe1 = d_lwe1; A.lwe2 = d_lwe2; A.draws = d_draws; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor;
+  A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_FINAL;
+  return launch_gates(c, A, (cudaStream_t)stream);
+}
+
+extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,
+                                     const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor) {
+  if (!c || !lwe1 || !lwe2 || !out_and || !out_or || !out_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t lwe_bytes = (size_t)batch * (c->hp.n + 1) * sizeof(uint64_t);
+  const size_t draw_bytes = draws ? (size_t)batch * c->hp.n * 4 * c->hp.m * sizeof(int64_t) : 0;
+  uint64_t* d_io = nullptr; int64_t* d_draws = nullptr;
+  if (cudaMalloc(&d_io, 5 * lwe_bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of LWE buffers failed");
+  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) { cudaFree(d_io); return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed"); }
+  const size_t w = lwe_bytes / sizeof(uint64_t);
+  int rc = SGFHE_OK;
+  cudaError_t e = cudaMemcpy(d_io, lwe1, lwe_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_io + w, lwe2, lwe_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = sgfhe_bootstrap_batch_device(c, batch, d_io, d_io + w, d_draws, d_io + 2 * w, d_io + 3 * w, d_io + 4 * w, nullptr);
+    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_and, d_io + 2 * w, lwe_bytes, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_or, d_io + 3 * w, lwe_bytes, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_xor, d_io + 4 * w, lwe_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_io); cudaFree(d_draws);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_batch: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bootstrap_trace(sgfhe_ctx* c, const uint64_t* lwe1, const uint64_t* lwe2, const int64_t* draws,
+                                     int32_t n_steps, uint64_t* trace, uint64_t* out_and, uint64_t* out_or,
+                                     uint64_t* out_xor) {
+  if (!c || !lwe1 || !lwe2 || !out_and || !out_or || !out_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (n_steps < 0 || n_steps > c->key_rows) return fail(n_steps < 0 ? SGFHE_ERR_ARG : SGFHE_ERR_STATE, "n_steps exceeds the uploaded key rows");
+  CK(cudaSetDevice(c->device));
+  const int n = c->hp.n, m = c->hp.m;
+  const size_t lwe_w = n + 1, tr_w = (size_t)2 * m * 2, dr_w = (size_t)4 * m;
+  uint64_t* d_buf = nullptr; int64_t* d_draws = nullptr;
+  const size_t words = 2 * lwe_w + 3 * lwe_w * 2 + (trace ? (size_t)n_steps * tr_w : 0);
+  if (cudaMalloc(&d_buf, words * sizeof(uint64_t)) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  if (draws && n_steps && cudaMalloc(&d_draws, (size_t)n_steps * dr_w * sizeof(int64_t)) != cudaSuccess) { cudaFree(d_buf); return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed"); }
+  uint64_t* d_l1 = d_buf; uint64_t* d_l2 = d_buf + lwe_w; uint64_t* d_out = d_buf + 2 * lwe_w; uint64_t* d_tr = d_out + 6 * lwe_w;
+  int rc = SGFHE_OK;
+  cudaError_t e = cudaMemcpy(d_l1, lwe1, lwe_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_l2, lwe2, lwe_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && d_draws) e = cudaMemcpy(d_draws, draws, (size_t)n_steps * dr_w * 8, cudaMemcpyHostToDevice);
+  // one launch per step so the accumulator can be copied out after each (test seam; the product path
+  // runs all n steps in one launch)
+  for (int k = -1; k < n_steps && rc == SGFHE_OK && e == cudaSuccess; ++k) {
+    GateArgs A; memset(&A, 0, sizeof A);
+    A.lwe1 = d_l1; A.lwe2 = d_l2; A.batch = 1;
+    A.out_and = d_out; A.out_or = d_out + 2 * lwe_w; A.out_xor = d_out + 4 * lwe_w;
+    if (k < 0) { A.flags = F_INIT; A.step_begin = A.step_end = 0; }
+    else {
+      A.step_begin = k; A.step_end = k + 1; A.draw_steps = 1;
+      A.draws = d_draws ? d_draws + (size_t)k * dr_w : nullptr;
+      A.trace = trace ? d_tr + (size_t)k * tr_w : nullptr;
+    }
+    if (k == n_steps - 1) A.flags |= F_FINAL | F_RAW;
+    rc = launch_gates(c, A, nullptr);
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_and, d_out, lwe_w * 16, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_or, d_out + 2 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_xor, d_out + 4 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess && trace && n_steps) e = cudaMemcpy(trace, d_tr, (size_t)n_steps * tr_w * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_buf); cudaFree(d_draws);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_trace: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_polymul_device(sgfhe_ctx* c, int32_t batch, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out,
+                                    void* stream) {
+  if (!c || !d_a || !d_b || !d_out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const int threads = c->hp.m / 4 < 128 ? 128 : (c->hp.m / 4 > 1024 ? 1024 : c->hp.m / 4);
+  const int cap = c->num_sms * 2;
+  const int grid = batch < cap ? batch : cap;
+  if (grid > c->pm_ctas) {
+    cudaFree(c->d_pm_scratch); c->d_pm_scratch = nullptr; c->pm_ctas = 0;
+    if (cudaMalloc(&c->d_pm_scratch, (size_t)grid * c->dc.LM * c->hp.m * sizeof(uint32_t)) != cudaSuccess)
+      return fail(SGFHE_ERR_NOMEM, "cudaMalloc of polymul scratch failed");
+    c->pm_ctas = grid;
+  }
+  polymul_kernel<<<grid, threads, (size_t)2 * c->hp.m * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      c->dc, d_a, d_b, d_out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_polymul(sgfhe_ctx* c, int32_t batch, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  if (!c || !a || !b || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)batch * c->hp.m * 16;
+  uint64_t* d = nullptr;
+  if (cudaMalloc(&d, 3 * bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  uint64_t* da = d; uint64_t* db = d + bytes / 8; uint64_t* dout = d + 2 * (bytes / 8);
+  int rc = SGFHE_OK;
+  cudaError_t e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { rc = sgfhe_polymul_device(c, batch, da, db, dout, nullptr); if (!rc) e = cudaDeviceSynchronize(); }
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("polymul: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_flatten_poly(sgfhe_ctx* c, const uint64_t* a, const int64_t* draws, uint64_t* out) {
+  if (!c || !a || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  const int m = c->hp.m;
+  uint64_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)m * (16 + 32 + 16)) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  uint64_t* da = d; uint64_t* dout = d + 2 * (size_t)m; int64_t* dd = reinterpret_cast<int64_t*>(d + 6 * (size_t)m);
+  cudaError_t e = cudaMemcpy(da, a, (size_t)m * 16, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && draws) e = cudaMemcpy(dd, draws, (size_t)m * 16, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    flatten_kernel<<<(m + 255) / 256, 256>>>(c->dc, da, draws ? dd : nullptr, dout);
+    ++g_launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)m * 32, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("flatten_poly: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_external_product(sgfhe_ctx* c, const uint64_t* a, const uint64_t* b, const uint64_t* Amat,
+                                      const int64_t* draws, uint64_t* a_out, uint64_t* b_out) {
+  if (!c || !a || !b || !Amat || !a_out || !b_out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  const int m = c->hp.m;
+  uint32_t* d_khat = nullptr; uint64_t* d_ab = nullptr; int64_t* d_draws = nullptr;
+  int rc = ensure_scratch(c, 1); if (rc) return rc;
+  if (cudaMalloc(&d_khat, keyhat_row_words(c) * sizeof(uint32_t)) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  if (cudaMalloc(&d_ab, (size_t)2 * m * 16 + 64) != cudaSuccess) { cudaFree(d_khat); return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed"); }
+  if (draws && cudaMalloc(&d_draws, (size_t)4 * m * 8) != cudaSuccess) { cudaFree(d_khat); cudaFree(d_ab); return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed"); }
+  rc = transform_polys(c, Amat, 0, 8, d_khat);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemcpy(d_ab, a, (size_t)m * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ab + 2 * (size_t)m, b, (size_t)m * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, (size_t)4 * m * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+      acc_load_kernel<<<(2 * m + 255) / 256, 256>>>(m, d_ab, reinterpret_cast<uint32_t*>(c->d_scratch));
+      ++g_launches;
+      uint64_t* dummy = d_ab + 4 * (size_t)m;     // lwe pointers are not dereferenced for u when F_EXT is set ... but
+      GateArgs A; memset(&A, 0, sizeof A);        // ... they are indexed for the pointer arithmetic only
+      A.lwe1 = dummy; A.lwe2 = dummy; A.batch = 1; A.step_begin = 0; A.step_end = 1; A.draw_steps = 1;
+      A.draws = d_draws; A.flags = F_EXT; A.trace = d_ab;
+      A.out_and = A.out_or = A.out_xor = dummy;
+      A.keyhat = d_khat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i; A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
+      bootstrap_kernel<<<1, c->threads, c->smem_bytes>>>(c->dc, A);
+      ++g_launches;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(a_out, d_ab, (size_t)m * 16, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(b_out, d_ab + 2 * (size_t)m, (size_t)m * 16, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_khat); cudaFree(d_ab); cudaFree(d_draws);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("external_product: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}

@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on identical inputs.
+
+Bar: bit-exact (all arithmetic on the path is integer).  Mirrors test/internals.test.jl and
+test/api.test.jl of the reference, plus per-step accumulator equality the reference cannot check.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env64(so, sg):
+    P = sg.Params(64)
+    OP = so.Params(64)
+    sk = so.make_secret(OP, 0)
+    key = so.make_bkey(OP, sk, 0)
+    bits, lwes = so.make_lwes(OP, sk, 0)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    return P, OP, sk, key, bits, lwes, bkey
+
+
+def _edge_polys(m, Q, so):
+    z = np.zeros((m, 2), np.uint64)
+    one = z.copy(); one[0, 0] = 1
+    top = z.copy(); top[m - 1, 0] = 1                       # x^(m-1)
+    full = np.broadcast_to(so.pack([Q - 1]), (m, 2)).copy()  # all coefficients Q-1
+    return [z, one, top, full]
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024])
+def test_polymul_matches_oracle(so, sg, n):
+    """DarkIntegers `Polynomial *` seam (called at src/fhe.jl:527-528): random and edge operands."""
+    P, OP = sg.Params(n), so.Params(n)
+    rng = np.random.default_rng(100 + n)
+    a = so.rand_below(rng, OP.Q, (6, OP.m))
+    b = so.rand_below(rng, OP.Q, (6, OP.m))
+    edges = _edge_polys(OP.m, OP.Q, so)
+    a = np.concatenate([a, np.stack(edges), np.stack(edges[::-1])])
+    b = np.concatenate([b, np.stack(edges), np.stack(edges)])
+    got = sg.polymul(P, a, b)
+    for i in range(a.shape[0]):
+        assert np.array_equal(got[i], so.polymul(a[i], b[i], OP.Q)), f"product {i}"
+    P.close()
+
+
+@pytest.mark.parametrize("n", [64, 512, 1024])
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_flatten_poly_matches_oracle(so, sg, n, use_rng):
+    """flatten_poly (src/utils.jl:253-264), port of test/internals.test.jl:115-141 plus exact equality."""
+    P, OP = sg.Params(n), so.Params(n)
+    rng = np.random.default_rng(200 + n)
+    a = so.rand_below(rng, OP.Q, (OP.m,))
+    a[0] = 0; a[1] = so.pack([OP.Q - 1])[0]; a[2] = so.pack([OP.B])[0]; a[3] = so.pack([OP.B - 1])[0]
+    xmax = OP.B // 2 * 3
+    draws = rng.integers(-xmax, xmax + 1, size=(OP.m, 2), dtype=np.int64) if use_rng else None
+    if use_rng:
+        draws[0] = (-xmax, xmax); draws[1] = (xmax, -xmax)
+    got = sg.flatten_poly(P, draws, a)
+    ref = so.flatten_poly(a, OP.B, 2, OP.Q, draws)
+    assert np.array_equal(got, ref)
+    # recomposition (test/internals.test.jl:138-140) and limits (:50-66)
+    gi = so.unpack(got)
+    for j in range(0, OP.m, 97):
+        assert (gi[0][j] + gi[1][j] * OP.B) % OP.Q == so.unpack(a[j:j + 1])[0]
+    P.close()
+
+
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_external_product_with_gadget_is_identity(so, sg, use_rng):
+    """port of test/internals.test.jl:144-166: (a,b) (.) G == (a,b)"""
+    P, OP = sg.Params(64), so.Params(64)
+    rng = np.random.default_rng(7)
+    a, b = so.rand_below(rng, OP.Q, (OP.m,)), so.rand_below(rng, OP.Q, (OP.m,))
+    G = np.zeros((4, 2, OP.m, 2), np.uint64)
+    G[0, 0, 0, 0] = 1; G[1, 0, 0, 0] = OP.B; G[2, 1, 0, 0] = 1; G[3, 1, 0, 0] = OP.B
+    xmax = OP.B // 2 * 3
+    draws = rng.integers(-xmax, xmax + 1, size=(2, OP.m, 2), dtype=np.int64) if use_rng else None
+    oa, ob = sg.external_product(P, draws, a, b, G)
+    assert np.array_equal(oa, a) and np.array_equal(ob, b)
+    P.close()
+
+
+@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_external_product_matches_oracle(so, sg, n, use_rng):
+    """external_product (src/fhe.jl:519-530) with a random full-size A"""
+    P, OP = sg.Params(n), so.Params(n)
+    rng = np.random.default_rng(300 + n)
+    a, b = so.rand_below(rng, OP.Q, (OP.m,)), so.rand_below(rng, OP.Q, (OP.m,))
+    A = so.rand_below(rng, OP.Q, (4, 2, OP.m))
+    xmax = OP.B // 2 * 3
+    draws = rng.integers(-xmax, xmax + 1, size=(2, OP.m, 2), dtype=np.int64) if use_rng else None
+    oa, ob = sg.external_product(P, draws, a, b, A)
+    ra, rb = so.external_product(a, b, A, OP.B, OP.Q, draws)
+    assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+    P.close()
+
+
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_bootstrap_trace_p64_every_step(env64, so, sg, use_rng):
+    """_bootstrap_internal (src/fhe.jl:559-595): accumulator after every one of the n steps and the three
+    output LWEs over Z_Q equal the oracle's LITERAL formulation."""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    rng = np.random.default_rng(11)
+    xmax = OP.B // 2 * 3
+    draws = rng.integers(-xmax, xmax + 1, size=(OP.n, 2, OP.m, 2), dtype=np.int64) if use_rng else None
+    for (i, j) in [(10, 20), (0, 63)]:
+        ga, go, gx, gtr = sg.bootstrap_trace(bkey, draws, lwes[i], lwes[j])
+        ra, ro, rx, rtr = so.bootstrap_internal(OP, key, lwes[i], lwes[j], draws=draws, trace=True)
+        for k in range(OP.n):
+            assert np.array_equal(gtr[k], rtr[k]), f"accumulator differs after step {k}"
+        assert np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
+
+
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_bootstrap_gates_p64(env64, so, sg, use_rng):
+    """port of test/api.test.jl:45-83: 32 disjoint bit pairs, rng and nothing; decrypt(AND/OR/XOR) is the
+    plaintext gate, and every output LWE equals the oracle's bootstrap() bit for bit."""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    l1, l2 = lwes[:32], lwes[32:64]
+    if use_rng:
+        rng = np.random.default_rng(21)
+        xmax = OP.B // 2 * 3
+        draws = rng.integers(-xmax, xmax + 1, size=(32, OP.n, 2, OP.m, 2), dtype=np.int64)
+        import ctypes as C
+        outs = [np.zeros_like(l1) for _ in range(3)]
+        from sgfhe_jl_b200 import _lib
+        bkey.upload()
+        _lib.check(_lib.lib().sgfhe_bootstrap_batch(P.ctx, 32, l1.ctypes.data_as(C.c_void_p), l2.ctypes.data_as(C.c_void_p),
+                                                    draws.ctypes.data_as(C.c_void_p), *[o.ctypes.data_as(C.c_void_p) for o in outs]))
+    else:
+        draws = None
+        outs = sg.bootstrap_batch(bkey, None, l1, l2)
+    for g in range(32):
+        y1, y2 = int(bits[g]), int(bits[32 + g])
+        assert so.decrypt_lwe(OP, sk, outs[0][g]) == (y1 & y2)
+        assert so.decrypt_lwe(OP, sk, outs[1][g]) == (y1 | y2)
+        assert so.decrypt_lwe(OP, sk, outs[2][g]) == (y1 ^ y2)
+    for g in range(0, 32, 5):
+        ref = so.bootstrap(OP, key, l1[g], l2[g], None if draws is None else draws[g])
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o[g], r)
+
+
+def test_bootstrap_is_deterministic_without_rng(env64, sg):
+    """docs/src/manual.md:155-169"""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    o1 = sg.bootstrap_batch(bkey, None, lwes[:4], lwes[4:8])
+    o2 = sg.bootstrap_batch(bkey, None, lwes[:4], lwes[4:8])
+    assert all(np.array_equal(a, b) for a, b in zip(o1, o2))
+
+
+def test_public_api_roundtrip_p64(sg):
+    """docs/src/index.md:14-39 through the mirrored API only (no oracle): keygen on the GPU, encrypt, split,
+    bootstrap bits 10 and 20, decrypt."""
+    rng = np.random.default_rng(5)
+    P = sg.Params(64)
+    sk = sg.PrivateKey(P, rng)
+    bkey = sg.BootstrapKey(rng, sk)
+    msg = rng.integers(0, 2, size=64, dtype=np.uint8)
+    ct = sg.encrypt(sk, rng, msg)
+    assert np.array_equal(sg.decrypt(sk, ct), msg.astype(bool))
+    ebits = sg.split_ciphertext(ct)
+    assert all(sg.decrypt(sk, e) == bool(b) for e, b in zip(ebits, msg))     # test/api.test.jl:33-42
+    for r in (None, rng):
+        a, o, x = sg.bootstrap(bkey, r, ebits[10], ebits[20])
+        y1, y2 = bool(msg[10]), bool(msg[20])
+        assert (sg.decrypt(sk, a), sg.decrypt(sk, o), sg.decrypt(sk, x)) == (y1 and y2, y1 or y2, y1 != y2)
+    P.close()
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+def test_bootstrap_trace_truncated_large(so, sg, n):
+    """paper-size parameters (86-bit Q, m = 8192): first steps of the loop against the oracle, both modes"""
+    P, OP = sg.Params(n), so.Params(n)
+    steps = 3
+    sk = so.make_secret(OP, 1)
+    key = so.make_bkey(OP, sk, 1, rows=steps)
+    bits, lwes = so.make_lwes(OP, sk, 1)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    rng = np.random.default_rng(31)
+    xmax = OP.B // 2 * 3
+    for draws in (None, rng.integers(-xmax, xmax + 1, size=(steps, 2, OP.m, 2), dtype=np.int64)):
+        ga, go, gx, gtr = sg.bootstrap_trace(bkey, draws, lwes[3], lwes[700 % n], n_steps=steps)
+        ra, ro, rx, rtr = so.bootstrap_internal(OP, key, lwes[3], lwes[700 % n], draws=draws, n_steps=steps, trace=True)
+        for k in range(steps):
+            assert np.array_equal(gtr[k], rtr[k]), f"accumulator differs after step {k}"
+        assert np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
+    P.close()
