@@ -25,11 +25,12 @@ struct DevConst {
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
   uint64_t barrett_mu;          // floor(2^(sbits+35) / Q)
+  uint32_t Ql[3], offl[3];      // Q and offs as 32-bit limbs
   uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP];
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
-  uint64_t dig_bias[MAXP];                  // multiple of p, >= 2^47
+  uint64_t dig_bias[MAXP];                  // multiple of p, >= 2^46
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
   uint32_t crt_c[2][MAXP][3];               // (P/p_i) mod Q, 32-bit limbs
   uint32_t negP[2][3];                      // (-P) mod Q
@@ -64,128 +65,214 @@ __device__ __forceinline__ uint32_t redc(uint64_t T, uint32_t p, uint32_t pinv_n
   return (uint32_t)((T + (uint64_t)mq * p) >> 32);
 }
 
-// ---- one radix-2^LOGR pass over `npoly` polynomials of N coefficients held in shared memory ---------
-// Active index bits are [b, b+LOGR).  Twiddle table: tw[i] = (psi^bitrev(i), Shoup companion), i in [1,N);
-// the butterfly on bit b' of element idx uses tw[(N + idx) >> (b'+1)].
-template <int LOGR, bool FWD>
-__device__ __forceinline__ void ntt_pass(uint32_t* sm, int npoly, int N, int b, const uint2* __restrict__ tw,
-                                         uint32_t p) {
+// radix-2^LOGR register blocks; w[(1<<l)-1+g] is the twiddle of group g at level l
+template <int LOGR>
+__device__ __forceinline__ void fwd_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2) {
   constexpr int R = 1 << LOGR;
-  const int nblk = N >> LOGR;
-  const int nthr = blockDim.x;
-  const int G = nblk < nthr ? nblk : nthr;
-  const int ngrp = nthr / G;
-  const int grp = threadIdx.x / G, lane = threadIdx.x - grp * G;
+#pragma unroll
+  for (int l = 0; l < LOGR; ++l) {
+    const int half = R >> (l + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << l); ++g)
+#pragma unroll
+      for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
+  }
+}
+template <int LOGR>
+__device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2) {
+  constexpr int R = 1 << LOGR;
+#pragma unroll
+  for (int l = LOGR - 1; l >= 0; --l) {
+    const int half = R >> (l + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << l); ++g)
+#pragma unroll
+      for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
+  }
+}
+
+// Compile-time shape of the on-chip transform of length M = 2^LOGM.
+//   REM   = LOGM % 3 top stages are fused into the phases that fill / drain shared memory;
+//   NPASS = LOGM / 3 radix-8 passes run over shared memory, active bits [3k, 3k+3);
+//   G threads own one polynomial (one radix-8 block each), NG polynomials are processed side by side.
+template <int LOGM>
+struct Shape {
+  static constexpr int M = 1 << LOGM;
+  static constexpr int REM = LOGM % 3;
+  static constexpr int NPASS = LOGM / 3;
+  static constexpr int G = M / 8;
+  static constexpr int T = (M / 2 > 1024) ? 1024 : M / 2;
+  static constexpr int NG = T / G;
+  static constexpr int STR = M >> REM;       // stride of the fused top stages
+};
+
+// One radix-8 pass (active bits [B, B+3)) over NPOLY polynomials in shared memory.
+// Twiddles: tw[i] = (psi^bitrev(i), Shoup companion); the butterfly on bit b' of element idx uses
+// tw[(M + idx) >> (b'+1)], so a block with base index `base` needs tw[t1], tw[2 t1 + {0,1}], tw[4 t1 + {0..3}].
+template <int LOGM, int NPOLY, bool FWD, int B>
+__device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
+  using S = Shape<LOGM>;
+  constexpr int M = S::M;
+  const int grp = threadIdx.x / S::G, lane = threadIdx.x % S::G;
+  if (grp >= NPOLY) return;
   const uint32_t p2 = 2 * p;
-  if (grp >= ngrp) return;
-  const int lowmask = (1 << b) - 1;
-  for (int blk = lane; blk < nblk; blk += G) {
-    const int base = ((blk & ~lowmask) << LOGR) | (blk & lowmask);
-    const int t1 = (N + base) >> (b + LOGR);
-    uint2 w[R - 1];
+  const int base = ((lane >> B) << (B + 3)) | (lane & ((1 << B) - 1));
+  const int t1 = (M >> (B + 3)) + (lane >> B);
+  uint2 w[7];
+  {
+    w[0] = __ldg(&tw[t1]);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(&tw[2 * t1]));
+    w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1]));
+    const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1 + 2]));
+    w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w);
+    w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
+  }
+  // swizzled addresses of the 8 elements (swz(): bits 3,4 ^= bits 6,7), hoisted out of the polynomial loop
+  int off[8];
+  if (B == 0) {
+    const int a0 = swz(base);
 #pragma unroll
-    for (int l = 0; l < LOGR; ++l)
+    for (int j = 0; j < 8; ++j) off[j] = a0 + j;
+  } else if (B == 3) {
+    const int s3 = ((base >> 6) & 3) << 3, clean = base;          // base has bits 3..5 clear
 #pragma unroll
-      for (int j = 0; j < (1 << l); ++j) w[(1 << l) - 1 + j] = __ldg(&tw[(t1 << l) + j]);
-    for (int poly = grp; poly < npoly; poly += ngrp) {
-      uint32_t* s = sm + poly * N;
-      uint32_t x[R];
-      if (LOGR == 3 && b == 0) {
-        const uint4* v = reinterpret_cast<const uint4*>(s + swz(base));
-        const uint4 v0 = v[0], v1 = v[1];
-        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-        x[4 % R] = v1.x; x[5 % R] = v1.y; x[6 % R] = v1.z; x[7 % R] = v1.w;
+    for (int j = 0; j < 8; ++j) off[j] = clean + (s3 ^ ((j & 3) << 3)) + ((j & 4) << 3);
+  } else if (B == 6) {                                            // base has bits 6..8 clear
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = (base ^ ((j & 3) << 3)) + (j << 6);
+  } else {
+    const int a0 = swz(base);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = a0 + (j << B);
+  }
+#pragma unroll
+  for (int q = 0; q < (NPOLY + S::NG - 1) / S::NG; ++q) {
+    const int poly = grp + q * S::NG;
+    if (poly < NPOLY) {
+      uint32_t* s = sm + poly * M;
+      uint32_t x[8];
+      if (B == 0) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(s + off[0]);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(s + off[4]);
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) x[j] = s[swz(base + (j << b))];
+        for (int j = 0; j < 8; ++j) x[j] = s[off[j]];
       }
-      if (FWD) {
-#pragma unroll
-        for (int l = 0; l < LOGR; ++l) {
-          const int half = R >> (l + 1);
-#pragma unroll
-          for (int g = 0; g < (1 << l); ++g)
-#pragma unroll
-            for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
-        }
+      if (FWD) fwd_block<3>(x, w, p, p2); else inv_block<3>(x, w, p, p2);
+      if (B == 0) {
+        *reinterpret_cast<uint4*>(s + off[0]) = make_uint4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<uint4*>(s + off[4]) = make_uint4(x[4], x[5], x[6], x[7]);
       } else {
 #pragma unroll
-        for (int l = LOGR - 1; l >= 0; --l) {
-          const int half = R >> (l + 1);
-#pragma unroll
-          for (int g = 0; g < (1 << l); ++g)
-#pragma unroll
-            for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
-        }
-      }
-      if (LOGR == 3 && b == 0) {
-        uint4* v = reinterpret_cast<uint4*>(s + swz(base));
-        v[0] = make_uint4(x[0], x[1], x[2], x[3]);
-        v[1] = make_uint4(x[4 % R], x[5 % R], x[6 % R], x[7 % R]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) s[swz(base + (j << b))] = x[j];
+        for (int j = 0; j < 8; ++j) s[off[j]] = x[j];
       }
     }
   }
 }
 
-// Negacyclic forward NTT of `npoly` polys in shared memory: natural order in (values in [0,4p)),
-// bit-reversed order out (values in [0,4p)).  Ends with __syncthreads().
-__device__ __forceinline__ void ntt_forward(uint32_t* sm, int npoly, int N, int logN, const uint2* __restrict__ tw,
-                                            uint32_t p) {
-  const int rem = logN % 3;
-  int b = logN - rem;
-  if (rem == 1) { ntt_pass<1, true>(sm, npoly, N, b, tw, p); __syncthreads(); }
-  if (rem == 2) { ntt_pass<2, true>(sm, npoly, N, b, tw, p); __syncthreads(); }
-  while (b > 0) { b -= 3; ntt_pass<3, true>(sm, npoly, N, b, tw, p); __syncthreads(); }
-}
-// Inverse: bit-reversed in (values in [0,2p)), natural out ([0,2p)), WITHOUT the 1/N factor.
-__device__ __forceinline__ void ntt_inverse(uint32_t* sm, int npoly, int N, int logN, const uint2* __restrict__ tw,
-                                            uint32_t p) {
-  const int rem = logN % 3;
-  const int top = logN - rem;
-  for (int b = 0; b < top; b += 3) { ntt_pass<3, false>(sm, npoly, N, b, tw, p); __syncthreads(); }
-  if (rem == 1) { ntt_pass<1, false>(sm, npoly, N, top, tw, p); __syncthreads(); }
-  if (rem == 2) { ntt_pass<2, false>(sm, npoly, N, top, tw, p); __syncthreads(); }
+template <int LOGM, int NPOLY, bool FWD, int K>
+struct PassLoop {
+  static __device__ __forceinline__ void run(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
+    constexpr int NP = Shape<LOGM>::NPASS;
+    constexpr int B = FWD ? 3 * (NP - 1 - K) : 3 * K;
+    ntt_pass8<LOGM, NPOLY, FWD, B>(sm, tw, p);
+    __syncthreads();
+    PassLoop<LOGM, NPOLY, FWD, K + 1>::run(sm, tw, p);
+  }
+};
+template <int LOGM, int NPOLY, bool FWD>
+struct PassLoop<LOGM, NPOLY, FWD, Shape<LOGM>::NPASS> {
+  static __device__ __forceinline__ void run(uint32_t*, const uint2* __restrict__, uint32_t) {}
+};
+// the NPASS radix-8 passes over bits [0, 3 NPASS); each pass ends with __syncthreads().
+// Forward: high bits first (after the fused REM top stages); inverse: low bits first.
+template <int LOGM, int NPOLY, bool FWD>
+__device__ __forceinline__ void ntt_passes(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
+  PassLoop<LOGM, NPOLY, FWD, 0>::run(sm, tw, p);
 }
 
-// ---- wide helpers --------------------------------------------------------------------------------------
+// uniform twiddles of the fused top stages: tw[1 .. 2^REM - 1]
+template <int REM>
+__device__ __forceinline__ void top_twiddles(const uint2* __restrict__ tw, uint2* w) {
+#pragma unroll
+  for (int k = 1; k < (1 << REM); ++k) w[k - 1] = __ldg(&tw[k]);
+}
+
+// ---- 96-bit limb arithmetic (Q < 2^93) ---------------------------------------------------------------
+struct u96 { uint32_t x0, x1, x2; };
+
+__device__ __forceinline__ u96 add96(u96 a, u96 b) {
+  u96 r;
+  asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+      : "=r"(r.x0), "=r"(r.x1), "=r"(r.x2) : "r"(a.x0), "r"(a.x1), "r"(a.x2), "r"(b.x0), "r"(b.x1), "r"(b.x2));
+  return r;
+}
+// r = a - b, borrow = 0xFFFFFFFF if a < b else 0
+__device__ __forceinline__ u96 sub96(u96 a, u96 b, uint32_t& borrow) {
+  u96 r;
+  asm("sub.cc.u32 %0, %4, %7;\n\tsubc.cc.u32 %1, %5, %8;\n\tsubc.cc.u32 %2, %6, %9;\n\tsubc.u32 %3, 0, 0;"
+      : "=r"(r.x0), "=r"(r.x1), "=r"(r.x2), "=r"(borrow)
+      : "r"(a.x0), "r"(a.x1), "r"(a.x2), "r"(b.x0), "r"(b.x1), "r"(b.x2));
+  return r;
+}
+__device__ __forceinline__ u96 sel96(bool c, u96 a, u96 b) { u96 r; r.x0 = c ? a.x0 : b.x0; r.x1 = c ? a.x1 : b.x1; r.x2 = c ? a.x2 : b.x2; return r; }
+__device__ __forceinline__ u96 Q96(const DevConst& C) { u96 q; q.x0 = C.Ql[0]; q.x1 = C.Ql[1]; q.x2 = C.Ql[2]; return q; }
+// x in [0, 2Q) -> [0, Q)
+__device__ __forceinline__ u96 csubQ(u96 x, u96 Q) { uint32_t bw; const u96 t = sub96(x, Q, bw); return sel96(bw != 0, x, t); }
+__device__ __forceinline__ u96 addmod96(u96 a, u96 b, u96 Q) { return csubQ(add96(a, b), Q); }
+__device__ __forceinline__ u96 submod96(u96 a, u96 b, u96 Q) { uint32_t bw; const u96 t = sub96(a, b, bw); return sel96(bw != 0, add96(t, Q), t); }
+__device__ __forceinline__ u96 negmod96(u96 a, u96 Q) { uint32_t bw; const u96 t = sub96(Q, a, bw); return sel96((a.x0 | a.x1 | a.x2) == 0, a, t); }
+__device__ __forceinline__ u128 to128(u96 a) { return (u128)a.x0 | ((u128)a.x1 << 32) | ((u128)a.x2 << 64); }
+__device__ __forceinline__ u96 from128(u128 v) { u96 r; r.x0 = (uint32_t)v; r.x1 = (uint32_t)(v >> 32); r.x2 = (uint32_t)(v >> 64); return r; }
+
+__device__ __forceinline__ u96 ld96(const uint32_t* base, int stride, int idx) {
+  u96 r; r.x0 = base[idx]; r.x1 = base[stride + idx]; r.x2 = base[2 * stride + idx]; return r;
+}
+__device__ __forceinline__ void st96(uint32_t* base, int stride, int idx, u96 v) {
+  base[idx] = v.x0; base[stride + idx] = v.x1; base[2 * stride + idx] = v.x2;
+}
+
+// ---- wide (u128) helpers: seams and one-off kernels only ------------------------------------------------
 __device__ __forceinline__ u128 addmodQ(u128 a, u128 b, u128 Q) { u128 s = a + b; return s >= Q ? s - Q : s; }
 __device__ __forceinline__ u128 submodQ(u128 a, u128 b, u128 Q) { return a >= b ? a - b : a + Q - b; }
 __device__ __forceinline__ u128 negmodQ(u128 a, u128 Q) { return a ? Q - a : (u128)0; }
 
-__device__ __forceinline__ u128 load3(const uint32_t* base, int stride, int idx) {
-  return (u128)base[idx] | ((u128)base[stride + idx] << 32) | ((u128)base[2 * stride + idx] << 64);
-}
-__device__ __forceinline__ void store3(uint32_t* base, int stride, int idx, u128 v) {
-  base[idx] = (uint32_t)v; base[stride + idx] = (uint32_t)(v >> 32); base[2 * stride + idx] = (uint32_t)(v >> 64);
+// flatten(nothing, a, Val(B), Val(2)) as signed digits (src/utils.jl:155-189); a in [0,Q)
+__device__ __forceinline__ void decompose_det(const DevConst& C, u96 a, u96 Q, int64_t& d0, int64_t& d1) {
+  u96 off; off.x0 = C.offl[0]; off.x1 = C.offl[1]; off.x2 = C.offl[2];
+  a = addmod96(a, off, Q);                        // a += offset             (src/utils.jl:179)
+  // divrem(a, B), B = 35 2^kB, 22 <= kB <= 38   (src/utils.jl:172)
+  const uint64_t lo64 = (uint64_t)a.x0 | ((uint64_t)a.x1 << 32);
+  const uint64_t hi64 = (uint64_t)a.x1 | ((uint64_t)a.x2 << 32);
+  const uint64_t t = C.kB >= 32 ? (hi64 >> (C.kB - 32)) : ((lo64 >> C.kB) | ((uint64_t)a.x2 << (64 - C.kB)));
+  const uint64_t lo = lo64 & ((1ull << C.kB) - 1);
+  const uint64_t u1 = t / 35u;
+  const uint64_t u0 = ((t - u1 * 35u) << C.kB) | lo;
+  d0 = (int64_t)(u0 - C.s);                       // - s                     (src/utils.jl:183-185)
+  d1 = (int64_t)(u1 - C.s);
 }
 
-// flatten(rng|nothing, a, Val(B), Val(2)) as signed digits (src/utils.jl:155-189, 198-241).
-// x0, x1 are the caller's draws (0, 0 for the deterministic form).
-__device__ __forceinline__ void decompose(const DevConst& C, u128 a, int64_t x0, int64_t x1, bool random,
+// flatten(rng, ...) (src/utils.jl:198-241): x0, x1 are the caller's draws
+__device__ __forceinline__ void decompose(const DevConst& C, u96 a, u96 Q, int64_t x0, int64_t x1, bool random,
                                           int64_t& d0, int64_t& d1) {
   if (random) {                                   // rand_a = a - x0 - x1 B   (src/utils.jl:222,232-233)
     i128 X = (i128)x1 * (i128)C.B + (i128)x0;
     X %= (i128)C.Q;
     if (X < 0) X += (i128)C.Q;
-    a = submodQ(a, (u128)X, C.Q);
+    a = from128(submodQ(to128(a), (u128)X, C.Q));
   }
-  a = addmodQ(a, C.offs, C.Q);                    // a += offset             (src/utils.jl:179)
-  const uint64_t t = (uint64_t)(a >> C.kB);       // divrem(a, B), B = 35 2^kB (src/utils.jl:172)
-  const uint64_t lo = (uint64_t)a & ((1ull << C.kB) - 1);
-  const uint64_t u1 = t / 35u;
-  const uint64_t u0 = ((t - u1 * 35u) << C.kB) | lo;
-  d0 = (int64_t)(u0 - C.s) + x0;                  // - s (+ x)               (src/utils.jl:183-185, 236-238)
-  d1 = (int64_t)(u1 - C.s) + x1;
+  decompose_det(C, a, Q, d0, d1);
+  d0 += x0;                                       // + x                     (src/utils.jl:236-238)
+  d1 += x1;
 }
 
-// signed digit (|d| < 2^46) -> residue mod p_i in [0,3p)
-__device__ __forceinline__ uint32_t digit_mod(const DevConst& C, int i, int64_t d) {
-  const uint64_t dp = (uint64_t)(d + (int64_t)C.dig_bias[i]);
-  const uint32_t q = __umulhi((uint32_t)(dp >> 18), C.dig_mu[i]);
-  return (uint32_t)dp - q * C.p[i];
+// signed digit (|d| < 2^46) -> residue mod p_i in [0,2p)
+__device__ __forceinline__ uint32_t digit_mod(int64_t d, uint64_t bias, uint32_t mu, uint32_t p) {
+  const uint64_t dp = (uint64_t)(d + (int64_t)bias);
+  const uint32_t q = __umulhi((uint32_t)(dp >> 18), mu);
+  return (uint32_t)dp - q * p;
 }
 
 // canonical value of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p)
@@ -199,7 +286,7 @@ __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c
 
 // CRT lift: residues y_i = z (P/p_i)^-1 mod p_i of an integer |z| < P/32  ->  z mod Q, canonical.
 template <int BASIS>
-__device__ __forceinline__ u128 crt_lift(const DevConst& C, int K, const uint32_t* y, size_t stride) {
+__device__ __forceinline__ u96 crt_lift(const DevConst& C, int K, const uint32_t* __restrict__ y, size_t stride) {
   uint64_t colA[3] = {0, 0, 0}, colB[3] = {0, 0, 0}, vs = 0;
 #pragma unroll
   for (int i = 0; i < MAXP; ++i) {
@@ -216,12 +303,35 @@ __device__ __forceinline__ u128 crt_lift(const DevConst& C, int K, const uint32_
   const uint32_t v = (uint32_t)((vs + (1u << 28)) >> 29);   // round(sum y_i / p_i)
 #pragma unroll
   for (int k = 0; k < 3; ++k) colB[k] += (uint64_t)v * C.negP[BASIS][k];
-  const u128 S = (u128)colA[0] + colB[0] + (((u128)colA[1] + colB[1]) << 32) + (((u128)colA[2] + colB[2]) << 64);
-  const uint64_t T = (uint64_t)(S >> (C.sbits - 29));
-  const uint64_t qh = __umul64hi(T, C.barrett_mu);
-  u128 R = S - (u128)qh * C.Q;
-  if (R >= C.Q) R -= C.Q;
-  if (R >= C.Q) R -= C.Q;
+  // S = sum_k (colA[k] + colB[k]) 2^(32k) < 2^126, as four limbs
+  uint32_t s0, s1, s2, s3;
+  {
+    const uint64_t c0 = colA[0] + colB[0]; const uint32_t k0 = c0 < colA[0];
+    const uint64_t c1 = colA[1] + colB[1]; const uint32_t k1 = c1 < colA[1];
+    const uint64_t c2 = colA[2] + colB[2];                    // top column cannot overflow (c_i[2] < 2^29)
+    s0 = (uint32_t)c0;
+    const uint64_t t1 = (c0 >> 32) + (uint32_t)c1;
+    s1 = (uint32_t)t1;
+    const uint64_t t2 = (t1 >> 32) + (c1 >> 32) + k0 + (uint32_t)c2;
+    s2 = (uint32_t)t2;
+    s3 = (uint32_t)((t2 >> 32) + (c2 >> 32) + k1);
+  }
+  // Barrett: qh = floor(floor(S / 2^(sbits-29)) mu / 2^64) in [S/Q - 2, S/Q]
+  const int sh = C.sbits - 29 - 32;                           // 0 <= sh < 32
+  const uint32_t tl = __funnelshift_r(s1, s2, sh), th = __funnelshift_r(s2, s3, sh);
+  const uint64_t qh = __umul64hi((uint64_t)tl | ((uint64_t)th << 32), C.barrett_mu);
+  const uint32_t q0 = (uint32_t)qh, q1 = (uint32_t)(qh >> 32);
+  const uint64_t m0 = (uint64_t)q0 * C.Ql[0];
+  const uint64_t m1 = (uint64_t)q0 * C.Ql[1] + (m0 >> 32);
+  const uint64_t m1b = (uint64_t)q1 * C.Ql[0] + (uint32_t)m1;
+  u96 prod; prod.x0 = (uint32_t)m0; prod.x1 = (uint32_t)m1b;
+  prod.x2 = q0 * C.Ql[2] + q1 * C.Ql[1] + (uint32_t)(m1 >> 32) + (uint32_t)(m1b >> 32);
+  u96 S; S.x0 = s0; S.x1 = s1; S.x2 = s2;
+  uint32_t bw;
+  const u96 Q = Q96(C);
+  u96 R = sub96(S, prod, bw);                                 // exact mod 2^96; true value in [0, 3Q)
+  R = csubQ(R, Q);
+  R = csubQ(R, Q);
   return R;
 }
 

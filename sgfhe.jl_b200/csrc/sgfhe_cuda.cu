@@ -20,7 +20,7 @@ using namespace sgfhe;
 // Kernels
 // =========================================================================================================
 
-enum : int { F_INIT = 1, F_FINAL = 2, F_RAW = 4, F_EXT = 8 };
+enum : int { F_INIT = 1, F_FINAL = 2, F_RAW = 4, F_EXT = 8, F_DECOMP = 16 };
 
 struct GateArgs {
   const uint64_t* lwe1; const uint64_t* lwe2;   // [batch][n+1] over Z_r
@@ -45,92 +45,133 @@ __device__ __forceinline__ Scratch carve(uint8_t* base, int m) {
 static size_t scratch_bytes(int m, int L) { return (size_t)(56 + 8 * L) * m; }
 
 // accumulator init: a = 0, b = t(x) x^(-u_b) DQ   (src/fhe.jl:566-573, t(x) from src/fhe.jl:535-548)
+template <int LOGM>
 __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
-  const int m = C.m;
+  constexpr int m = 1 << LOGM;
+  const u96 DQ = from128(C.DQ), nDQ = from128(C.Q - C.DQ);
+  u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     const int src = (int)((j + ub) & (uint64_t)(2 * m - 1));
     const int idx = src & (m - 1);
     int sgn = idx < m / 2 ? 1 : (idx == m / 2 ? 0 : -1);     // Dr = m/2: +1 on [0,m/2), 0, -1 on (m/2,m)
     if (src >= m) sgn = -sgn;
-    const u128 v = sgn == 0 ? (u128)0 : (sgn > 0 ? C.DQ : C.Q - C.DQ);
-    store3(S.acc, m, j, 0);
-    store3(S.acc + 3 * m, m, j, v);
+    st96(S.acc, m, j, zero);
+    st96(S.acc + 3 * m, m, j, sgn == 0 ? zero : (sgn > 0 ? DQ : nDQ));
   }
 }
 
-// One accumulation step (body of src/fhe.jl:579-582).  u = rotation amount in [0, 2m).
+// gadget decomposition of accumulator polynomial c (src/utils.jl:253-264) into S.dig[2c], S.dig[2c+1]
+template <int LOGM>
+__device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch& S, int c, const int64_t* __restrict__ draws) {
+  constexpr int m = 1 << LOGM;
+  const u96 Q = Q96(C);
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+    const u96 v = ld96(S.acc + c * 3 * m, m, idx);
+    int64_t d0, d1;
+    if (draws) decompose(C, v, Q, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], true, d0, d1);
+    else decompose_det(C, v, Q, d0, d1);
+    S.dig[(2 * c) * m + idx] = d0;
+    S.dig[(2 * c + 1) * m + idx] = d1;
+  }
+}
+
+// One accumulation step (body of src/fhe.jl:579-582) on digits already in S.dig; leaves the new accumulator in
+// S.acc and its decomposition (with `draws_next`, the following step's draws) in S.dig.  u = rotation in [0, 2m).
+template <int LOGM>
 __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                           const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
-                          const int64_t* __restrict__ draws, int u, bool ext) {
-  const int m = C.m, nthr = blockDim.x, tid = threadIdx.x;
-  // Phase A: gadget decomposition of both accumulator polynomials (src/utils.jl:253-264; a then b)
-  for (int idx = tid; idx < m; idx += nthr) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const u128 v = load3(S.acc + c * 3 * m, m, idx);
-      int64_t x0 = 0, x1 = 0, d0, d1;
-      if (draws) { x0 = draws[((size_t)c * m + idx) * 2]; x1 = draws[((size_t)c * m + idx) * 2 + 1]; }
-      decompose(C, v, x0, x1, draws != nullptr, d0, d1);
-      S.dig[(2 * c) * m + idx] = d0;
-      S.dig[(2 * c + 1) * m + idx] = d1;
-    }
-  }
-  __syncthreads();
+                          const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next) {
+  using SH = Shape<LOGM>;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T;
+  const int tid = threadIdx.x;
   // Phase B: per RNS prime -- 4 forward NTTs, 8 MACs against the key tile, 2 inverse NTTs
   for (int i = 0; i < C.L; ++i) {
-    const uint32_t p = C.p[i];
-    for (int e = tid; e < 4 * m; e += nthr) {
-      const int j = e >> C.logm, idx = e & (m - 1);
-      sm[j * m + swz(idx)] = digit_mod(C, i, S.dig[e]);
+    const uint32_t p = C.p[i], p2 = 2 * p;
+    {
+      const uint64_t bias = C.dig_bias[i]; const uint32_t mu = C.dig_mu[i];
+      uint2 wt[R > 1 ? R - 1 : 1];
+      top_twiddles<REM>(tw_f + (size_t)i * m, wt);
+#pragma unroll 4
+      for (int e = tid; e < 4 * STR; e += T) {
+        const int j = e / STR, idx = e % STR;
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.dig[j * m + idx + k * STR], bias, mu, p);
+        fwd_block<REM>(x, wt, p, p2);
+#pragma unroll
+        for (int k = 0; k < R; ++k) sm[j * m + swz(idx + k * STR)] = x[k];
+      }
     }
     __syncthreads();
-    ntt_forward(sm, 4, m, C.logm, tw_f + (size_t)i * m, p);
+    ntt_passes<LOGM, 4, true>(sm, tw_f + (size_t)i * m, p);
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
-    for (int idx = tid; idx < m; idx += nthr) {
+    const uint32_t pinv = C.pinv_neg[i];
+#pragma unroll 2
+    for (int idx = tid; idx < m; idx += T) {
       uint64_t sa = 0, sb = 0;
+      const int si = swz(idx);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t d = sm[j * m + swz(idx)];
-        d = min(d, d - 2 * p); d = min(d, d - p);
+        uint32_t d = sm[j * m + si];
+        d = min(d, d - p2); d = min(d, d - p);
         sa += (uint64_t)d * __ldg(&K[(2 * j) * m + idx]);
         sb += (uint64_t)d * __ldg(&K[(2 * j + 1) * m + idx]);
       }
-      sm[swz(idx)] = redc(sa, p, C.pinv_neg[i]);
-      sm[m + swz(idx)] = redc(sb, p, C.pinv_neg[i]);
+      sm[si] = redc(sa, p, pinv);
+      sm[m + si] = redc(sb, p, pinv);
     }
     __syncthreads();
-    ntt_inverse(sm, 2, m, C.logm, tw_i + (size_t)i * m, p);
-    for (int e = tid; e < 2 * m; e += nthr) {
-      const int c = e >> C.logm, idx = e & (m - 1);
-      const uint32_t y = shoup_mul(sm[c * m + swz(idx)], C.scale[0][i], C.scale_sh[0][i], p);
-      S.zres[((size_t)i * 2 + c) * m + idx] = csub(y, p);
+    ntt_passes<LOGM, 2, false>(sm, tw_i + (size_t)i * m, p);
+    {
+      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i];
+      uint2 wt[R > 1 ? R - 1 : 1];
+      top_twiddles<REM>(tw_i + (size_t)i * m, wt);
+#pragma unroll 4
+      for (int e = tid; e < 2 * STR; e += T) {
+        const int c = e / STR, idx = e % STR;
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = sm[c * m + swz(idx + k * STR)];
+        inv_block<REM>(x, wt, p, p2);
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(shoup_mul(x[k], sc, scs, p), p);
+      }
     }
     __syncthreads();
   }
-  // Phase C: CRT lift to Z_Q
-  for (int e = tid; e < 2 * m; e += nthr) {
-    const int c = e >> C.logm, idx = e & (m - 1);
-    const u128 z = crt_lift<0>(C, C.L, S.zres + (size_t)c * m + idx, (size_t)2 * m);
-    store3(S.zq + c * 3 * m, m, idx, z);
-  }
-  __syncthreads();
-  // Phase D: acc += x^u z - z   (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product)
-  for (int e = tid; e < 2 * m; e += nthr) {
-    const int c = e >> C.logm, j = e & (m - 1);
-    const u128 z = load3(S.zq + c * 3 * m, m, j);
-    u128 res;
-    if (ext) {
-      res = z;
-    } else {
-      const int src = (j - u) & (2 * m - 1);
-      u128 zr = load3(S.zq + c * 3 * m, m, src & (m - 1));
-      if (src >= m) zr = negmodQ(zr, C.Q);
-      const u128 acc = load3(S.acc + c * 3 * m, m, j);
-      res = addmodQ(acc, submodQ(zr, z, C.Q), C.Q);
+  // Phase C/D per accumulator polynomial: CRT lift into shared memory, then acc += x^u z - z
+  // (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product) and the next step's decomposition.
+  const u96 Q = Q96(C);
+  for (int c = 0; c < 2; ++c) {
+#pragma unroll 2
+    for (int idx = tid; idx < m; idx += T)
+      st96(sm, m, idx, crt_lift<0>(C, C.L, S.zres + (size_t)c * m + idx, (size_t)2 * m));
+    __syncthreads();
+    uint32_t* acc = S.acc + c * 3 * m;
+#pragma unroll 2
+    for (int j = tid; j < m; j += T) {
+      const u96 z = ld96(sm, m, j);
+      u96 res;
+      if (ext) {
+        res = z;
+      } else {
+        const int src = (j - u) & (2 * m - 1);
+        u96 zr = ld96(sm, m, src & (m - 1));
+        if (src >= m) zr = negmod96(zr, Q);
+        res = addmod96(ld96(acc, m, j), submod96(zr, z, Q), Q);
+      }
+      st96(acc, m, j, res);
+      if (decompose_next) {
+        int64_t d0, d1;
+        if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
+        else decompose_det(C, res, Q, d0, d1);
+        S.dig[(2 * c) * m + j] = d0;
+        S.dig[(2 * c + 1) * m + j] = d1;
+      }
     }
-    store3(S.acc + c * 3 * m, m, j, res);
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // extract + AND/OR/XOR assembly (src/fhe.jl:585-592) + reduce_modulus (src/fhe.jl:616-618)
@@ -140,13 +181,13 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
   for (int k = threadIdx.x; k <= n; k += blockDim.x) {
     u128 va, vo;
     if (k < n) {
-      va = load3(S.acc, m, 3 * m / 4 - k);                           // extract(a, 3m/4+1, n)[k]
-      vo = negmodQ(load3(S.acc, m, m / 4 - k), C.Q);                 // -extract(a, m/4+1, n)[k]
+      va = to128(ld96(S.acc, m, 3 * m / 4 - k));                           // extract(a, 3m/4+1, n)[k]
+      vo = negmodQ(to128(ld96(S.acc, m, m / 4 - k)), C.Q);                 // -extract(a, m/4+1, n)[k]
     } else {
-      va = addmodQ(C.DQ, load3(S.acc + 3 * m, m, 3 * m / 4), C.Q);   // DQ + b[3m/4]
-      vo = submodQ(C.DQ, load3(S.acc + 3 * m, m, m / 4), C.Q);       // DQ - b[m/4]
+      va = addmodQ(C.DQ, to128(ld96(S.acc + 3 * m, m, 3 * m / 4)), C.Q);   // DQ + b[3m/4]
+      vo = submodQ(C.DQ, to128(ld96(S.acc + 3 * m, m, m / 4)), C.Q);       // DQ - b[m/4]
     }
-    const u128 vx = submodQ(vo, va, C.Q);                            // a_or - a_and
+    const u128 vx = submodQ(vo, va, C.Q);                                  // a_or - a_and
     if (raw) {
       out_and[2 * k] = (uint64_t)va; out_and[2 * k + 1] = (uint64_t)(va >> 64);
       out_or[2 * k] = (uint64_t)vo; out_or[2 * k + 1] = (uint64_t)(vo >> 64);
@@ -157,26 +198,37 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
   }
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// F_DECOMP: (re)compute S.dig from S.acc before the first step of this launch (set with F_INIT, and by the
+// trace / external-product seams whose accumulator arrives from a previous launch or from the host).
+template <int LOGM>
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
 bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
   extern __shared__ __align__(16) uint32_t sm[];
-  const int m = C.m, n = C.n;
+  constexpr int m = 1 << LOGM;
+  const int n = C.n;
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
-    if (A.flags & F_INIT) gate_init(C, S, (l1[n] + l2[n]) & rmask);
+    const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
+    if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
+    __syncthreads();
+    if ((A.flags & F_DECOMP) && A.step_begin < A.step_end) {
+      decompose_poly<LOGM>(C, S, 0, dr);
+      decompose_poly<LOGM>(C, S, 1, dr);
+    }
     __syncthreads();
     for (int k = A.step_begin; k < A.step_end; ++k) {
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
-      const int64_t* dr = A.draws ? A.draws + ((size_t)g * A.draw_steps + (k - A.step_begin)) * 4 * m : nullptr;
-      gate_step(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i, dr, u, (A.flags & F_EXT) != 0);
+      const bool more = k + 1 < A.step_end;
+      gate_step<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i,
+                      (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more);
     }
     if (A.trace) {
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
-        const u128 v = load3(S.acc + (e / m) * 3 * m, m, e % m);
-        A.trace[2 * e] = (uint64_t)v; A.trace[2 * e + 1] = (uint64_t)(v >> 64);
+        const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
+        A.trace[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); A.trace[2 * e + 1] = v.x2;
       }
     }
     if (A.flags & F_FINAL) {
@@ -190,61 +242,93 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
 
 // Key pre-transform (K10): coefficient-form wide polys -> per-prime NTT domain, Montgomery form.
 // grid = (npolys, L).  coef: [npolys][m][2];  out: poly P of row k=P/8, slot jc=P%8 -> keyhat[((k L + i) 8 + jc) m ..]
-__global__ void __launch_bounds__(1024, 1)
+template <int LOGM>
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
 key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ coef, uint32_t* __restrict__ keyhat,
                      const uint2* __restrict__ tw_f, int poly0) {
   extern __shared__ __align__(16) uint32_t sm[];
-  const int m = C.m, i = blockIdx.y;
-  const uint32_t p = C.p[i];
+  using SH = Shape<LOGM>;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
+  const int i = blockIdx.y;
+  const uint32_t p = C.p[i], p2 = 2 * p;
   const uint64_t* src = coef + (size_t)blockIdx.x * m * 2;
-  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-    const u128 c = (u128)src[2 * idx] | ((u128)src[2 * idx + 1] << 64);
-    sm[swz(idx)] = centred_mod(C, i, c);
+  uint2 wt[R > 1 ? R - 1 : 1];
+  top_twiddles<REM>(tw_f + (size_t)i * m, wt);
+  for (int idx = threadIdx.x; idx < STR; idx += blockDim.x) {
+    uint32_t x[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int e = idx + k * STR;
+      x[k] = centred_mod(C, i, (u128)src[2 * e] | ((u128)src[2 * e + 1] << 64));
+    }
+    fwd_block<REM>(x, wt, p, p2);
+#pragma unroll
+    for (int k = 0; k < R; ++k) sm[swz(idx + k * STR)] = x[k];
   }
   __syncthreads();
-  ntt_forward(sm, 1, m, C.logm, tw_f + (size_t)i * m, p);
+  ntt_passes<LOGM, 1, true>(sm, tw_f + (size_t)i * m, p);
   const int P = poly0 + blockIdx.x, k = P >> 3, jc = P & 7;
   uint32_t* dst = keyhat + (((size_t)k * C.L + i) * 8 + jc) * m;
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     uint32_t v = sm[swz(idx)];
-    v = min(v, v - 2 * p); v = min(v, v - p);
+    v = min(v, v - p2); v = min(v, v - p);
     dst[idx] = csub(shoup_mul(v, C.mont[i], C.mont_sh[i], p), p);
   }
 }
 
 // Standalone negacyclic product of two full-size operands (seam for DarkIntegers `Polynomial *`).
 // grid = batch CTAs; scratch per CTA: [LM][m] u32.
-__global__ void __launch_bounds__(1024, 1)
+template <int LOGM>
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
 polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
                uint32_t* scratch, int batch) {
   extern __shared__ __align__(16) uint32_t sm[];
-  const int m = C.m;
+  using SH = Shape<LOGM>;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
   uint32_t* zres = scratch + (size_t)blockIdx.x * C.LM * m;
   for (int g = blockIdx.x; g < batch; g += gridDim.x) {
-    const uint64_t* pa = a + (size_t)g * m * 2; const uint64_t* pb = b + (size_t)g * m * 2;
     for (int i = 0; i < C.LM; ++i) {
-      const uint32_t p = C.p[i];
-      for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-        sm[swz(idx)] = centred_mod(C, i, (u128)pa[2 * idx] | ((u128)pa[2 * idx + 1] << 64));
-        sm[m + swz(idx)] = centred_mod(C, i, (u128)pb[2 * idx] | ((u128)pb[2 * idx + 1] << 64));
+      const uint32_t p = C.p[i], p2 = 2 * p;
+      uint2 wt[R > 1 ? R - 1 : 1];
+      top_twiddles<REM>(tw_f + (size_t)i * m, wt);
+      for (int e = threadIdx.x; e < 2 * STR; e += blockDim.x) {
+        const int c = e / STR, idx = e % STR;
+        const uint64_t* src = (c ? b : a) + (size_t)g * m * 2;
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+          const int q = idx + k * STR;
+          x[k] = centred_mod(C, i, (u128)src[2 * q] | ((u128)src[2 * q + 1] << 64));
+        }
+        fwd_block<REM>(x, wt, p, p2);
+#pragma unroll
+        for (int k = 0; k < R; ++k) sm[c * m + swz(idx + k * STR)] = x[k];
       }
       __syncthreads();
-      ntt_forward(sm, 2, m, C.logm, tw_f + (size_t)i * m, p);
+      ntt_passes<LOGM, 2, true>(sm, tw_f + (size_t)i * m, p);
       for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
         uint32_t x = sm[swz(idx)], y = sm[m + swz(idx)];
-        x = min(x, x - 2 * p); x = min(x, x - p); y = min(y, y - 2 * p); y = min(y, y - p);
+        x = min(x, x - p2); x = min(x, x - p); y = min(y, y - p2); y = min(y, y - p);
         sm[swz(idx)] = redc((uint64_t)x * y, p, C.pinv_neg[i]);
       }
       __syncthreads();
-      ntt_inverse(sm, 1, m, C.logm, tw_i + (size_t)i * m, p);
-      for (int idx = threadIdx.x; idx < m; idx += blockDim.x)
-        zres[(size_t)i * m + idx] = csub(shoup_mul(sm[swz(idx)], C.scale[1][i], C.scale_sh[1][i], p), p);
+      ntt_passes<LOGM, 1, false>(sm, tw_i + (size_t)i * m, p);
+      top_twiddles<REM>(tw_i + (size_t)i * m, wt);
+      for (int idx = threadIdx.x; idx < STR; idx += blockDim.x) {
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = sm[swz(idx + k * STR)];
+        inv_block<REM>(x, wt, p, p2);
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          zres[(size_t)i * m + idx + k * STR] = csub(shoup_mul(x[k], C.scale[1][i], C.scale_sh[1][i], p), p);
+      }
       __syncthreads();
     }
     for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-      const u128 z = crt_lift<1>(C, C.LM, zres + idx, (size_t)m);
-      out[((size_t)g * m + idx) * 2] = (uint64_t)z; out[((size_t)g * m + idx) * 2 + 1] = (uint64_t)(z >> 64);
+      const u96 z = crt_lift<1>(C, C.LM, zres + idx, (size_t)m);
+      out[((size_t)g * m + idx) * 2] = (uint64_t)z.x0 | ((uint64_t)z.x1 << 32); out[((size_t)g * m + idx) * 2 + 1] = z.x2;
     }
     __syncthreads();
   }
@@ -257,7 +341,7 @@ __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_
   if (idx >= C.m) return;
   const u128 v = (u128)a[2 * idx] | ((u128)a[2 * idx + 1] << 64);
   int64_t d[2];
-  decompose(C, v, draws ? draws[2 * idx] : 0, draws ? draws[2 * idx + 1] : 0, draws != nullptr, d[0], d[1]);
+  decompose(C, from128(v), Q96(C), draws ? draws[2 * idx] : 0, draws ? draws[2 * idx + 1] : 0, draws != nullptr, d[0], d[1]);
   for (int i = 0; i < 2; ++i) {
     const u128 r = d[i] >= 0 ? (u128)d[i] : C.Q - (u128)(-d[i]);
     out[((size_t)i * C.m + idx) * 2] = (uint64_t)r; out[((size_t)i * C.m + idx) * 2 + 1] = (uint64_t)(r >> 64);
@@ -269,7 +353,7 @@ __global__ void acc_load_kernel(int m, const uint64_t* __restrict__ ab, uint32_t
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 2 * m) return;
   const u128 v = (u128)ab[2 * e] | ((u128)ab[2 * e + 1] << 64);
-  store3(acc + (e / m) * 3 * m, m, e % m, v);
+  st96(acc + (e / m) * 3 * m, m, e % m, from128(v));
 }
 
 // =========================================================================================================
@@ -319,6 +403,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   const u128 s = hp.B / 2 - 1;                       // B is even (src/utils.jl:162-166)
   dc->s = (uint64_t)s;
   dc->offs = h_mulmod(s, (1 + hp.B) % hp.Q, hp.Q);
+  to_limbs(hp.Q, dc->Ql); to_limbs(dc->offs, dc->offl);
   dc->barrett_mu = (uint64_t)(((u128)1 << (dc->sbits + 35)) / hp.Q);
   const int NP = L > LM ? L : LM;
   for (int i = 0; i < NP; ++i) {
@@ -368,6 +453,44 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   return 0;
 }
 
+
+// ---- LOGM dispatch: every kernel is compiled for m = 512 .. 8192 -------------------------------------------
+#define SGFHE_DISPATCH(logm, STMT)                         \
+  switch (logm) {                                          \
+    case 9:  { constexpr int LOGM_ = 9;  STMT; } break;    \
+    case 10: { constexpr int LOGM_ = 10; STMT; } break;    \
+    case 11: { constexpr int LOGM_ = 11; STMT; } break;    \
+    case 12: { constexpr int LOGM_ = 12; STMT; } break;    \
+    default: { constexpr int LOGM_ = 13; STMT; } break;    \
+  }
+
+static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
+  cudaError_t e = cudaSuccess;
+  SGFHE_DISPATCH(c->hp.logm, {
+    c->threads = Shape<LOGM_>::T;
+    e = cudaFuncSetAttribute(bootstrap_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(key_transform_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(polymul_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel<LOGM_>, c->threads, c->smem_bytes);
+  });
+  return e;
+}
+static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, const GateArgs& A) {
+  SGFHE_DISPATCH(c->hp.logm, (bootstrap_kernel<LOGM_><<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A)));
+  ++g_launches;
+}
+static void launch_key_transform(const sgfhe_ctx* c, int npolys, const uint64_t* d_coef, uint32_t* d_keyhat, int poly0) {
+  SGFHE_DISPATCH(c->hp.logm, (key_transform_kernel<LOGM_><<<dim3(npolys, c->dc.L), c->threads, (size_t)c->hp.m * 4>>>(
+                                  c->dc, d_coef, d_keyhat, c->d_tw_f, poly0)));
+  ++g_launches;
+}
+static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                           int batch) {
+  SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 8, st>>>(
+                                  c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch)));
+  ++g_launches;
+}
+
 extern "C" const char* sgfhe_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t sgfhe_launch_count(void) { return g_launches.load(); }
 
@@ -409,13 +532,9 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   const int m = hp.m;
-  c->threads = m / 2 < 128 ? 128 : (m / 2 > 1024 ? 1024 : m / 2);     // 4 polys x m/8 radix-8 blocks
   c->smem_bytes = (size_t)4 * m * sizeof(uint32_t);
-  CK(cudaFuncSetAttribute(bootstrap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-  CK(cudaFuncSetAttribute(key_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-  CK(cudaFuncSetAttribute(polymul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bootstrap_kernel, c->threads, c->smem_bytes));
+  CK(configure_kernels(c, &occ));
   if (occ < 1) { delete c; return fail(SGFHE_ERR_CUDA, "bootstrap kernel does not fit on an SM"); }
   c->max_ctas = occ * c->num_sms;
   c->scratch_stride = (scratch_bytes(m, c->dc.L) + 255) & ~(size_t)255;
@@ -473,8 +592,7 @@ static int transform_polys(sgfhe_ctx* c, const uint64_t* h_coef, int poly0, int 
     const int cnt = npolys - done < chunk ? npolys - done : chunk;
     cudaError_t e = cudaMemcpy(d_stage, h_coef + (size_t)done * m * 2, (size_t)cnt * poly_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-      key_transform_kernel<<<dim3(cnt, c->dc.L), c->threads, c->smem_bytes>>>(c->dc, d_stage, d_keyhat, c->d_tw_f, poly0 + done);
-      ++g_launches;
+      launch_key_transform(c, cnt, d_stage, d_keyhat, poly0 + done);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -515,8 +633,7 @@ static int launch_gates(sgfhe_ctx* c, GateArgs& A, cudaStream_t st) {
   int rc = ensure_scratch(c, grid); if (rc) return rc;
   A.keyhat = c->d_keyhat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i;
   A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
-  bootstrap_kernel<<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A);
-  ++g_launches;
+  launch_bootstrap(c, grid, st, A);
   CK(cudaGetLastError());
   return SGFHE_OK;
 }
@@ -531,7 +648,7 @@ extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const u
   CK(cudaSetDevice(c->device));
   GateArgs A; memset(&A, 0, sizeof A);
   A.lwe1 = d_lwe1; A.lwe2 = d_lwe2; A.draws = d_draws; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor;
-  A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_FINAL;
+  A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL;
   return launch_gates(c, A, (cudaStream_t)stream);
 }
 
@@ -590,7 +707,7 @@ extern "C" int sgfhe_bootstrap_trace(sgfhe_ctx* c, const uint64_t* lwe1, const u
     A.out_and = d_out; A.out_or = d_out + 2 * lwe_w; A.out_xor = d_out + 4 * lwe_w;
     if (k < 0) { A.flags = F_INIT; A.step_begin = A.step_end = 0; }
     else {
-      A.step_begin = k; A.step_end = k + 1; A.draw_steps = 1;
+      A.step_begin = k; A.step_end = k + 1; A.draw_steps = 1; A.flags = F_DECOMP;
       A.draws = d_draws ? d_draws + (size_t)k * dr_w : nullptr;
       A.trace = trace ? d_tr + (size_t)k * tr_w : nullptr;
     }
@@ -614,7 +731,6 @@ extern "C" int sgfhe_polymul_device(sgfhe_ctx* c, int32_t batch, const uint64_t*
   if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
   if (batch == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
-  const int threads = c->hp.m / 4 < 128 ? 128 : (c->hp.m / 4 > 1024 ? 1024 : c->hp.m / 4);
   const int cap = c->num_sms * 2;
   const int grid = batch < cap ? batch : cap;
   if (grid > c->pm_ctas) {
@@ -623,9 +739,7 @@ extern "C" int sgfhe_polymul_device(sgfhe_ctx* c, int32_t batch, const uint64_t*
       return fail(SGFHE_ERR_NOMEM, "cudaMalloc of polymul scratch failed");
     c->pm_ctas = grid;
   }
-  polymul_kernel<<<grid, threads, (size_t)2 * c->hp.m * sizeof(uint32_t), (cudaStream_t)stream>>>(
-      c->dc, d_a, d_b, d_out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch);
-  ++g_launches;
+  launch_polymul(c, grid, (cudaStream_t)stream, d_a, d_b, d_out, batch);
   CK(cudaGetLastError());
   return SGFHE_OK;
 }
@@ -692,11 +806,10 @@ extern "C" int sgfhe_external_product(sgfhe_ctx* c, const uint64_t* a, const uin
       uint64_t* dummy = d_ab + 4 * (size_t)m;     // lwe pointers are not dereferenced for u when F_EXT is set ... but
       GateArgs A; memset(&A, 0, sizeof A);        // ... they are indexed for the pointer arithmetic only
       A.lwe1 = dummy; A.lwe2 = dummy; A.batch = 1; A.step_begin = 0; A.step_end = 1; A.draw_steps = 1;
-      A.draws = d_draws; A.flags = F_EXT; A.trace = d_ab;
+      A.draws = d_draws; A.flags = F_EXT | F_DECOMP; A.trace = d_ab;
       A.out_and = A.out_or = A.out_xor = dummy;
       A.keyhat = d_khat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i; A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
-      bootstrap_kernel<<<1, c->threads, c->smem_bytes>>>(c->dc, A);
-      ++g_launches;
+      launch_bootstrap(c, 1, nullptr, A);
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
