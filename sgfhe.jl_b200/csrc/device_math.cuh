@@ -22,6 +22,7 @@ struct DevConst {
   int L;                        // primes used by the bootstrap external product
   int LM;                       // primes used by a general product of two full-size operands
   int sbits;                    // bits(Q) - 1
+  uint32_t zero;                // always 0; a constant-bank operand ptxas cannot fold (forces 3-input IADD3 on the ALU pipe)
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
   uint64_t barrett_mu;          // floor(2^(sbits+35) / Q)
@@ -30,14 +31,16 @@ struct DevConst {
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
-  uint64_t dig_bias[MAXP];                  // multiple of p, >= 2^46
+  uint32_t dig_negc[MAXP];                  // p - (2^46 mod p)
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
   uint32_t crt_c[2][MAXP][3];               // (P/p_i) mod Q, 32-bit limbs
   uint32_t negP[2][3];                      // (-P) mod Q
 };
 
 // ---- swizzled shared-memory index: keeps every radix-8 pass bank-conflict free ---------------------
-__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 6) & 3) << 3); }
+// bits 3,4 ^= bits 6,7 (scalar accesses of the stride-8 / stride-64 passes); bit 2 ^= bit 5 (the two 16-byte
+// halves a thread reads in the stride-1 pass land in different bank groups within a quarter warp).
+__device__ __forceinline__ int swz(int i) { return i ^ (((i >> 6) & 3) << 3) ^ (((i >> 5) & 1) << 2); }
 
 // ---- 32-bit modular primitives (p < 2^30) -----------------------------------------------------------
 // Shoup: x any 32-bit value, w < p, wsh = floor(w 2^32 / p)  ->  x*w mod p in [0, 2p)
@@ -47,15 +50,16 @@ __device__ __forceinline__ uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t w
 __device__ __forceinline__ uint32_t csub(uint32_t x, uint32_t p) { return min(x, x - p); }   // [0,2p) -> [0,p)
 
 // Harvey butterflies.  Forward (Cooley-Tukey): x in [0,4p), y any -> both in [0,4p).
-__device__ __forceinline__ void ct_bfly(uint32_t& x, uint32_t& y, uint2 w, uint32_t p, uint32_t p2) {
+// `z` is DevConst::zero: x + t + z compiles to IADD3 (ALU pipe) instead of IMAD.IADD (the saturated FMA pipe).
+__device__ __forceinline__ void ct_bfly(uint32_t& x, uint32_t& y, uint2 w, uint32_t p, uint32_t p2, uint32_t z) {
   const uint32_t xr = min(x, x - p2);
   const uint32_t t = shoup_mul(y, w.x, w.y, p);
-  x = xr + t;
+  x = xr + t + z;
   y = xr - t + p2;
 }
 // Inverse (Gentleman-Sande): x, y in [0,2p) -> both in [0,2p).
-__device__ __forceinline__ void gs_bfly(uint32_t& x, uint32_t& y, uint2 w, uint32_t p, uint32_t p2) {
-  const uint32_t s = x + y, d = x - y + p2;
+__device__ __forceinline__ void gs_bfly(uint32_t& x, uint32_t& y, uint2 w, uint32_t p, uint32_t p2, uint32_t z) {
+  const uint32_t s = x + y + z, d = x - y + p2;
   x = min(s, s - p2);
   y = shoup_mul(d, w.x, w.y, p);
 }
@@ -67,7 +71,7 @@ __device__ __forceinline__ uint32_t redc(uint64_t T, uint32_t p, uint32_t pinv_n
 
 // radix-2^LOGR register blocks; w[(1<<l)-1+g] is the twiddle of group g at level l
 template <int LOGR>
-__device__ __forceinline__ void fwd_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2) {
+__device__ __forceinline__ void fwd_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
   for (int l = 0; l < LOGR; ++l) {
@@ -75,11 +79,11 @@ __device__ __forceinline__ void fwd_block(uint32_t (&x)[1 << LOGR], const uint2*
 #pragma unroll
     for (int g = 0; g < (1 << l); ++g)
 #pragma unroll
-      for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
+      for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
   }
 }
 template <int LOGR>
-__device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2) {
+__device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
   for (int l = LOGR - 1; l >= 0; --l) {
@@ -87,8 +91,41 @@ __device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2*
 #pragma unroll
     for (int g = 0; g < (1 << l); ++g)
 #pragma unroll
-      for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2);
+      for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
   }
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded spin (a lost copy traps instead of hanging the GPU)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+// one elected thread: stage `bytes` (multiple of 16) of a twiddle table into shared memory
+__device__ __forceinline__ void stage_table(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of dst are done (barrier before)
+  mbar_expect_tx(bar, bytes);
+  constexpr uint32_t CH = 16384;
+  for (uint32_t o = 0; o < bytes; o += CH)
+    bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o < CH ? bytes - o : CH, bar);
 }
 
 // Compile-time shape of the on-chip transform of length M = 2^LOGM.
@@ -110,7 +147,7 @@ struct Shape {
 // Twiddles: tw[i] = (psi^bitrev(i), Shoup companion); the butterfly on bit b' of element idx uses
 // tw[(M + idx) >> (b'+1)], so a block with base index `base` needs tw[t1], tw[2 t1 + {0,1}], tw[4 t1 + {0..3}].
 template <int LOGM, int NPOLY, bool FWD, int B>
-__device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
+__device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
   using S = Shape<LOGM>;
   constexpr int M = S::M;
   const int grp = threadIdx.x / S::G, lane = threadIdx.x % S::G;
@@ -120,32 +157,18 @@ __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* __restrict_
   const int t1 = (M >> (B + 3)) + (lane >> B);
   uint2 w[7];
   {
-    w[0] = __ldg(&tw[t1]);
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(&tw[2 * t1]));
+    w[0] = tw[t1];
+    const uint4 a = *reinterpret_cast<const uint4*>(&tw[2 * t1]);
     w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
-    const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1]));
-    const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1 + 2]));
+    const uint4 b0 = *reinterpret_cast<const uint4*>(&tw[4 * t1]);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(&tw[4 * t1 + 2]);
     w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w);
     w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
   }
-  // swizzled addresses of the 8 elements (swz(): bits 3,4 ^= bits 6,7), hoisted out of the polynomial loop
+  // swizzled addresses of the 8 elements, hoisted out of the polynomial loop
   int off[8];
-  if (B == 0) {
-    const int a0 = swz(base);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = a0 + j;
-  } else if (B == 3) {
-    const int s3 = ((base >> 6) & 3) << 3, clean = base;          // base has bits 3..5 clear
-#pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = clean + (s3 ^ ((j & 3) << 3)) + ((j & 4) << 3);
-  } else if (B == 6) {                                            // base has bits 6..8 clear
-#pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = (base ^ ((j & 3) << 3)) + (j << 6);
-  } else {
-    const int a0 = swz(base);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = a0 + (j << B);
-  }
+  for (int j = 0; j < 8; ++j) off[j] = swz(base + (j << B));
 #pragma unroll
   for (int q = 0; q < (NPOLY + S::NG - 1) / S::NG; ++q) {
     const int poly = grp + q * S::NG;
@@ -160,7 +183,7 @@ __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = s[off[j]];
       }
-      if (FWD) fwd_block<3>(x, w, p, p2); else inv_block<3>(x, w, p, p2);
+      if (FWD) fwd_block<3>(x, w, p, p2, z); else inv_block<3>(x, w, p, p2, z);
       if (B == 0) {
         *reinterpret_cast<uint4*>(s + off[0]) = make_uint4(x[0], x[1], x[2], x[3]);
         *reinterpret_cast<uint4*>(s + off[4]) = make_uint4(x[4], x[5], x[6], x[7]);
@@ -174,23 +197,25 @@ __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* __restrict_
 
 template <int LOGM, int NPOLY, bool FWD, int K>
 struct PassLoop {
-  static __device__ __forceinline__ void run(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
+  static __device__ __forceinline__ void run(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
     constexpr int NP = Shape<LOGM>::NPASS;
     constexpr int B = FWD ? 3 * (NP - 1 - K) : 3 * K;
-    ntt_pass8<LOGM, NPOLY, FWD, B>(sm, tw, p);
-    __syncthreads();
-    PassLoop<LOGM, NPOLY, FWD, K + 1>::run(sm, tw, p);
+    ntt_pass8<LOGM, NPOLY, FWD, B>(sm, tw, p, z);
+    // bits [0,6) of the index stay inside one group of 8 consecutive threads (one warp): the stride-8 and
+    // stride-1 passes exchange data only within that group, so a warp-level barrier separates them.
+    if ((FWD && B == 3) || (!FWD && B == 0 && NP > 1)) __syncwarp(); else __syncthreads();
+    PassLoop<LOGM, NPOLY, FWD, K + 1>::run(sm, tw, p, z);
   }
 };
 template <int LOGM, int NPOLY, bool FWD>
 struct PassLoop<LOGM, NPOLY, FWD, Shape<LOGM>::NPASS> {
-  static __device__ __forceinline__ void run(uint32_t*, const uint2* __restrict__, uint32_t) {}
+  static __device__ __forceinline__ void run(uint32_t*, const uint2*, uint32_t, uint32_t) {}
 };
 // the NPASS radix-8 passes over bits [0, 3 NPASS); each pass ends with __syncthreads().
 // Forward: high bits first (after the fused REM top stages); inverse: low bits first.
 template <int LOGM, int NPOLY, bool FWD>
-__device__ __forceinline__ void ntt_passes(uint32_t* sm, const uint2* __restrict__ tw, uint32_t p) {
-  PassLoop<LOGM, NPOLY, FWD, 0>::run(sm, tw, p);
+__device__ __forceinline__ void ntt_passes(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
+  PassLoop<LOGM, NPOLY, FWD, 0>::run(sm, tw, p, z);
 }
 
 // uniform twiddles of the fused top stages: tw[1 .. 2^REM - 1]
@@ -268,11 +293,14 @@ __device__ __forceinline__ void decompose(const DevConst& C, u96 a, u96 Q, int64
   d1 += x1;
 }
 
-// signed digit (|d| < 2^46) -> residue mod p_i in [0,2p)
-__device__ __forceinline__ uint32_t digit_mod(int64_t d, uint64_t bias, uint32_t mu, uint32_t p) {
-  const uint64_t dp = (uint64_t)(d + (int64_t)bias);
-  const uint32_t q = __umulhi((uint32_t)(dp >> 18), mu);
-  return (uint32_t)dp - q * p;
+// Signed digits (|d| < 2^46) are stored biased, dp = d + 2^46, as two words: lo = dp mod 2^32, hi = dp >> 18.
+__device__ __forceinline__ void digit_pack(int64_t d, uint32_t& lo, uint32_t& hi) {
+  const uint64_t dp = (uint64_t)(d + ((int64_t)1 << 46));
+  lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18);
+}
+// residue of the digit mod p in [0,3p): mu = floor(2^50 / p), negc = p - (2^46 mod p)
+__device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t mu, uint32_t negc, uint32_t p) {
+  return lo - __umulhi(hi, mu) * p + negc;
 }
 
 // canonical value of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p)

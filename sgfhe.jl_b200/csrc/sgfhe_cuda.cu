@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,14 +32,15 @@ struct GateArgs {
   const uint2* tw_f; const uint2* tw_i;         // [MAXP][m]
   uint8_t* scratch; size_t scratch_stride;      // per CTA
   int batch, step_begin, step_end, draw_steps, flags;
+  unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
 };
 
-struct Scratch { uint32_t* acc; int64_t* dig; uint32_t* zq; uint32_t* zres; };
+struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; uint32_t* zres; };
 __device__ __forceinline__ Scratch carve(uint8_t* base, int m) {
   Scratch s;
   s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
-  s.dig = reinterpret_cast<int64_t*>(base + (size_t)24 * m);          // [4][m]
-  s.zq = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);          // [2][3][m], aliases dig
+  s.diglo = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);       // [4][m]
+  s.dighi = reinterpret_cast<uint32_t*>(base + (size_t)40 * m);       // [4][m]
   s.zres = reinterpret_cast<uint32_t*>(base + (size_t)56 * m);        // [L][2][m]
   return s;
 }
@@ -70,8 +72,9 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
     int64_t d0, d1;
     if (draws) decompose(C, v, Q, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], true, d0, d1);
     else decompose_det(C, v, Q, d0, d1);
-    S.dig[(2 * c) * m + idx] = d0;
-    S.dig[(2 * c + 1) * m + idx] = d1;
+    uint32_t lo, hi;
+    digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + idx] = lo; S.dighi[(2 * c) * m + idx] = hi;
+    digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + idx] = lo; S.dighi[(2 * c + 1) * m + idx] = hi;
   }
 }
 
@@ -80,15 +83,19 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
 template <int LOGM>
 __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                           const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
-                          const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next) {
+                          const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
+                          uint2* tab, uint64_t* bar, uint32_t& parity, unsigned long long* timing) {
   using SH = Shape<LOGM>;
+  long long tprev = timing ? clock64() : 0;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T;
   const int tid = threadIdx.x;
   // Phase B: per RNS prime -- 4 forward NTTs, 8 MACs against the key tile, 2 inverse NTTs
   for (int i = 0; i < C.L; ++i) {
     const uint32_t p = C.p[i], p2 = 2 * p;
+    if (tid == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);      // TMA: forward twiddles of this prime
     {
-      const uint64_t bias = C.dig_bias[i]; const uint32_t mu = C.dig_mu[i];
+      const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_f + (size_t)i * m, wt);
 #pragma unroll 4
@@ -96,32 +103,51 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
         const int j = e / STR, idx = e % STR;
         uint32_t x[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.dig[j * m + idx + k * STR], bias, mu, p);
-        fwd_block<REM>(x, wt, p, p2);
+        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.diglo[j * m + idx + k * STR], S.dighi[j * m + idx + k * STR], mu, negc, p);
+        fwd_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k) sm[j * m + swz(idx + k * STR)] = x[k];
       }
     }
     __syncthreads();
-    ntt_passes<LOGM, 4, true>(sm, tw_f + (size_t)i * m, p);
+    mbar_wait(bar, parity); parity ^= 1;
+    SGFHE_TICK(0);
+    ntt_passes<LOGM, 4, true>(sm, tab, p, C.zero);
+    if (tid == 0) stage_table(tab, tw_i + (size_t)i * m, m * 8, bar);      // TMA: inverse twiddles, under the pointwise phase
+    SGFHE_TICK(1);
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     const uint32_t pinv = C.pinv_neg[i];
-#pragma unroll 2
-    for (int idx = tid; idx < m; idx += T) {
-      uint64_t sa = 0, sb = 0;
-      const int si = swz(idx);
+    {
+      uint32_t kn[8];                                    // software pipeline: next index's key words in flight
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t d = sm[j * m + si];
-        d = min(d, d - p2); d = min(d, d - p);
-        sa += (uint64_t)d * __ldg(&K[(2 * j) * m + idx]);
-        sb += (uint64_t)d * __ldg(&K[(2 * j + 1) * m + idx]);
+      for (int q = 0; q < 8; ++q) kn[q] = __ldg(&K[q * m + tid]);
+#pragma unroll 1
+      for (int idx = tid; idx < m; idx += T) {
+        uint32_t kc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) kc[q] = kn[q];
+        if (idx + T < m) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) kn[q] = __ldg(&K[q * m + idx + T]);
+        }
+        uint64_t sa = 0, sb = 0;
+        const int si = swz(idx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t d = sm[j * m + si];
+          d = min(d, d - p2); d = min(d, d - p);
+          sa += (uint64_t)d * kc[2 * j];
+          sb += (uint64_t)d * kc[2 * j + 1];
+        }
+        sm[si] = redc(sa, p, pinv);
+        sm[m + si] = redc(sb, p, pinv);
       }
-      sm[si] = redc(sa, p, pinv);
-      sm[m + si] = redc(sb, p, pinv);
     }
     __syncthreads();
-    ntt_passes<LOGM, 2, false>(sm, tw_i + (size_t)i * m, p);
+    mbar_wait(bar, parity); parity ^= 1;
+    SGFHE_TICK(2);
+    ntt_passes<LOGM, 2, false>(sm, tab, p, C.zero);
+    SGFHE_TICK(3);
     {
       const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i];
       uint2 wt[R > 1 ? R - 1 : 1];
@@ -132,25 +158,44 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
         uint32_t x[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) x[k] = sm[c * m + swz(idx + k * STR)];
-        inv_block<REM>(x, wt, p, p2);
+        inv_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k)
           S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(shoup_mul(x[k], sc, scs, p), p);
       }
     }
     __syncthreads();
+    SGFHE_TICK(4);
   }
   // Phase C/D per accumulator polynomial: CRT lift into shared memory, then acc += x^u z - z
   // (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product) and the next step's decomposition.
   const u96 Q = Q96(C);
   for (int c = 0; c < 2; ++c) {
-#pragma unroll 2
-    for (int idx = tid; idx < m; idx += T)
-      st96(sm, m, idx, crt_lift<0>(C, C.L, S.zres + (size_t)c * m + idx, (size_t)2 * m));
+    {
+      const uint32_t* zr = S.zres + (size_t)c * m;
+      uint32_t yn[MAXP];                                 // next index's residues in flight
+#pragma unroll
+      for (int i = 0; i < MAXP; ++i) yn[i] = i < C.L ? zr[(size_t)i * 2 * m + tid] : 0;
+#pragma unroll 1
+      for (int idx = tid; idx < m; idx += T) {
+        uint32_t yc[MAXP];
+#pragma unroll
+        for (int i = 0; i < MAXP; ++i) yc[i] = yn[i];
+        if (idx + T < m) {
+#pragma unroll
+          for (int i = 0; i < MAXP; ++i) if (i < C.L) yn[i] = zr[(size_t)i * 2 * m + idx + T];
+        }
+        st96(sm, m, idx, crt_lift<0>(C, C.L, yc, 1));
+      }
+    }
     __syncthreads();
+    SGFHE_TICK(5);
     uint32_t* acc = S.acc + c * 3 * m;
-#pragma unroll 2
+    u96 an = ld96(acc, m, tid);                          // next index's accumulator limbs in flight
+#pragma unroll 1
     for (int j = tid; j < m; j += T) {
+      const u96 a = an;
+      if (j + T < m) an = ld96(acc, m, j + T);
       const u96 z = ld96(sm, m, j);
       u96 res;
       if (ext) {
@@ -159,19 +204,22 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
         const int src = (j - u) & (2 * m - 1);
         u96 zr = ld96(sm, m, src & (m - 1));
         if (src >= m) zr = negmod96(zr, Q);
-        res = addmod96(ld96(acc, m, j), submod96(zr, z, Q), Q);
+        res = addmod96(a, submod96(zr, z, Q), Q);
       }
       st96(acc, m, j, res);
       if (decompose_next) {
         int64_t d0, d1;
         if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
         else decompose_det(C, res, Q, d0, d1);
-        S.dig[(2 * c) * m + j] = d0;
-        S.dig[(2 * c + 1) * m + j] = d1;
+        uint32_t lo, hi;
+        digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
+        digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
       }
     }
     __syncthreads();
+    SGFHE_TICK(6);
   }
+#undef SGFHE_TICK
 }
 
 // extract + AND/OR/XOR assembly (src/fhe.jl:585-592) + reduce_modulus (src/fhe.jl:616-618)
@@ -206,6 +254,11 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int m = 1 << LOGM;
   const int n = C.n;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);                 // staged twiddle table of the current (prime, direction)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
@@ -223,7 +276,8 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
       const bool more = k + 1 < A.step_end;
       gate_step<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i,
-                      (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more);
+                      (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
+                      tab, bar, parity, blockIdx.x == 0 ? A.timing : nullptr);
     }
     if (A.trace) {
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
@@ -251,6 +305,11 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
   const int i = blockIdx.y;
   const uint32_t p = C.p[i], p2 = 2 * p;
+  uint2* tab = reinterpret_cast<uint2*>(sm + m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 3 * m);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
   const uint64_t* src = coef + (size_t)blockIdx.x * m * 2;
   uint2 wt[R > 1 ? R - 1 : 1];
   top_twiddles<REM>(tw_f + (size_t)i * m, wt);
@@ -261,12 +320,13 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
       const int e = idx + k * STR;
       x[k] = centred_mod(C, i, (u128)src[2 * e] | ((u128)src[2 * e + 1] << 64));
     }
-    fwd_block<REM>(x, wt, p, p2);
+    fwd_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
     for (int k = 0; k < R; ++k) sm[swz(idx + k * STR)] = x[k];
   }
   __syncthreads();
-  ntt_passes<LOGM, 1, true>(sm, tw_f + (size_t)i * m, p);
+  mbar_wait(bar, 0);
+  ntt_passes<LOGM, 1, true>(sm, tab, p, C.zero);
   const int P = poly0 + blockIdx.x, k = P >> 3, jc = P & 7;
   uint32_t* dst = keyhat + (((size_t)k * C.L + i) * 8 + jc) * m;
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
@@ -287,9 +347,15 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
   using SH = Shape<LOGM>;
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
   uint32_t* zres = scratch + (size_t)blockIdx.x * C.LM * m;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 2 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 4 * m);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
   for (int g = blockIdx.x; g < batch; g += gridDim.x) {
     for (int i = 0; i < C.LM; ++i) {
       const uint32_t p = C.p[i], p2 = 2 * p;
+      if (threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_f + (size_t)i * m, wt);
       for (int e = threadIdx.x; e < 2 * STR; e += blockDim.x) {
@@ -301,25 +367,28 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
           const int q = idx + k * STR;
           x[k] = centred_mod(C, i, (u128)src[2 * q] | ((u128)src[2 * q + 1] << 64));
         }
-        fwd_block<REM>(x, wt, p, p2);
+        fwd_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k) sm[c * m + swz(idx + k * STR)] = x[k];
       }
       __syncthreads();
-      ntt_passes<LOGM, 2, true>(sm, tw_f + (size_t)i * m, p);
+      mbar_wait(bar, parity); parity ^= 1;
+      ntt_passes<LOGM, 2, true>(sm, tab, p, C.zero);
+      if (threadIdx.x == 0) stage_table(tab, tw_i + (size_t)i * m, m * 8, bar);
       for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
         uint32_t x = sm[swz(idx)], y = sm[m + swz(idx)];
         x = min(x, x - p2); x = min(x, x - p); y = min(y, y - p2); y = min(y, y - p);
         sm[swz(idx)] = redc((uint64_t)x * y, p, C.pinv_neg[i]);
       }
       __syncthreads();
-      ntt_passes<LOGM, 1, false>(sm, tw_i + (size_t)i * m, p);
+      mbar_wait(bar, parity); parity ^= 1;
+      ntt_passes<LOGM, 1, false>(sm, tab, p, C.zero);
       top_twiddles<REM>(tw_i + (size_t)i * m, wt);
       for (int idx = threadIdx.x; idx < STR; idx += blockDim.x) {
         uint32_t x[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) x[k] = sm[swz(idx + k * STR)];
-        inv_block<REM>(x, wt, p, p2);
+        inv_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k)
           zres[(size_t)i * m + idx + k * STR] = csub(shoup_mul(x[k], C.scale[1][i], C.scale_sh[1][i], p), p);
@@ -418,7 +487,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     dc->qmodp[i] = (uint32_t)(hp.Q % p);
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
-    dc->dig_bias[i] = (uint64_t)p * ((((uint64_t)1 << 46) + p - 1) / p);
+    dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p);
   }
   for (int basis = 0; basis < 2; ++basis) {
     const int K = basis == 0 ? L : LM;
@@ -480,13 +549,13 @@ static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, cons
   ++g_launches;
 }
 static void launch_key_transform(const sgfhe_ctx* c, int npolys, const uint64_t* d_coef, uint32_t* d_keyhat, int poly0) {
-  SGFHE_DISPATCH(c->hp.logm, (key_transform_kernel<LOGM_><<<dim3(npolys, c->dc.L), c->threads, (size_t)c->hp.m * 4>>>(
+  SGFHE_DISPATCH(c->hp.logm, (key_transform_kernel<LOGM_><<<dim3(npolys, c->dc.L), c->threads, (size_t)c->hp.m * 12 + 16>>>(
                                   c->dc, d_coef, d_keyhat, c->d_tw_f, poly0)));
   ++g_launches;
 }
 static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const uint64_t* a, const uint64_t* b, uint64_t* out,
                            int batch) {
-  SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 8, st>>>(
+  SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 16 + 16, st>>>(
                                   c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch)));
   ++g_launches;
 }
@@ -532,7 +601,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   const int m = hp.m;
-  c->smem_bytes = (size_t)4 * m * sizeof(uint32_t);
+  c->smem_bytes = (size_t)24 * m + 16;                       // 4 NTT buffers + staged twiddle table + mbarrier
   int occ = 0;
   CK(configure_kernels(c, &occ));
   if (occ < 1) { delete c; return fail(SGFHE_ERR_CUDA, "bootstrap kernel does not fit on an SM"); }
@@ -649,6 +718,18 @@ extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const u
   GateArgs A; memset(&A, 0, sizeof A);
   A.lwe1 = d_lwe1; A.lwe2 = d_lwe2; A.draws = d_draws; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor;
   A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL;
+  if (getenv("SGFHE_PHASE_TIMING")) {            // profiling aid: per-phase cycles of CTA 0, printed to stderr
+    unsigned long long* d_t = nullptr; unsigned long long h_t[8] = {0};
+    CK(cudaMalloc(&d_t, sizeof h_t)); CK(cudaMemset(d_t, 0, sizeof h_t));
+    A.timing = d_t;
+    int rc = launch_gates(c, A, (cudaStream_t)stream);
+    CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h_t, d_t, sizeof h_t, cudaMemcpyDeviceToHost)); cudaFree(d_t);
+    static const char* names[7] = {"digit load+top stage", "forward passes", "pointwise", "inverse passes", "top stage+store", "crt", "update+decompose"};
+    unsigned long long tot = 0; for (int i = 0; i < 7; ++i) tot += h_t[i];
+    for (int i = 0; i < 7; ++i) fprintf(stderr, "[sgfhe phase] %-22s %12llu cycles  %5.1f%%\n", names[i], h_t[i], 100.0 * h_t[i] / (tot ? tot : 1));
+    fprintf(stderr, "[sgfhe phase] total %llu cycles over %d steps = %.0f cycles/step\n", tot, c->hp.n, (double)tot / c->hp.n);
+    return rc;
+  }
   return launch_gates(c, A, (cudaStream_t)stream);
 }
 
