@@ -33,6 +33,7 @@ struct GateArgs {
   uint8_t* scratch; size_t scratch_stride;      // per CTA
   int batch, step_begin, step_end, draw_steps, flags;
   unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
+  int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
 
 struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; uint32_t* zres; };
@@ -98,15 +99,35 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
       const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_f + (size_t)i * m, wt);
-#pragma unroll 4
-      for (int e = tid; e < 4 * STR; e += T) {
-        const int j = e / STR, idx = e % STR;
-        uint32_t x[R];
+      // register double buffering: the loads of batch b+1 are in flight while batch b is reduced and stored
+      constexpr int ITER = 4 * STR / T, U = ITER >= 4 ? 4 : ITER, NBATCH = ITER / U;
+      uint32_t lo[2][U][R], hi[2][U][R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.diglo[j * m + idx + k * STR], S.dighi[j * m + idx + k * STR], mu, negc, p);
-        fwd_block<REM>(x, wt, p, p2, C.zero);
+      for (int q = 0; q < U; ++q) {
+        const int e = tid + q * T, j = e / STR, idx = e % STR;
 #pragma unroll
-        for (int k = 0; k < R; ++k) sm[j * m + swz(idx + k * STR)] = x[k];
+        for (int k = 0; k < R; ++k) { lo[0][q][k] = S.diglo[j * m + idx + k * STR]; hi[0][q][k] = S.dighi[j * m + idx + k * STR]; }
+      }
+#pragma unroll
+      for (int b = 0; b < NBATCH; ++b) {
+        if (b + 1 < NBATCH) {
+#pragma unroll
+          for (int q = 0; q < U; ++q) {
+            const int e = tid + ((b + 1) * U + q) * T, j = e / STR, idx = e % STR;
+#pragma unroll
+            for (int k = 0; k < R; ++k) { lo[(b + 1) & 1][q][k] = S.diglo[j * m + idx + k * STR]; hi[(b + 1) & 1][q][k] = S.dighi[j * m + idx + k * STR]; }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+          const int e = tid + (b * U + q) * T, j = e / STR, idx = e % STR;
+          uint32_t x[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) x[k] = digit_mod(lo[b & 1][q][k], hi[b & 1][q][k], mu, negc, p);
+          fwd_block<REM>(x, wt, p, p2, C.zero);
+#pragma unroll
+          for (int k = 0; k < R; ++k) sm[j * m + swz(idx + k * STR)] = x[k];
+        }
       }
     }
     __syncthreads();
@@ -118,17 +139,17 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     const uint32_t pinv = C.pinv_neg[i];
     {
-      uint32_t kn[8];                                    // software pipeline: next index's key words in flight
+      // software pipeline: the key words of the next two indices are in flight while one index is multiplied
+      constexpr int NIT = m / T;
+      uint32_t kq[3][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) kn[q] = __ldg(&K[q * m + tid]);
-#pragma unroll 1
-      for (int idx = tid; idx < m; idx += T) {
-        uint32_t kc[8];
+      for (int q = 0; q < 8; ++q) { kq[0][q] = __ldg(&K[q * m + tid]); if (NIT > 1) kq[1][q] = __ldg(&K[q * m + tid + T]); }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) kc[q] = kn[q];
-        if (idx + T < m) {
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = tid + it * T;
+        if (it + 2 < NIT) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) kn[q] = __ldg(&K[q * m + idx + T]);
+          for (int q = 0; q < 8; ++q) kq[(it + 2) % 3][q] = __ldg(&K[q * m + idx + 2 * T]);
         }
         uint64_t sa = 0, sb = 0;
         const int si = swz(idx);
@@ -136,8 +157,8 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
         for (int j = 0; j < 4; ++j) {
           uint32_t d = sm[j * m + si];
           d = min(d, d - p2); d = min(d, d - p);
-          sa += (uint64_t)d * kc[2 * j];
-          sb += (uint64_t)d * kc[2 * j + 1];
+          sa += (uint64_t)d * kq[it % 3][2 * j];
+          sb += (uint64_t)d * kq[it % 3][2 * j + 1];
         }
         sm[si] = redc(sa, p, pinv);
         sm[m + si] = redc(sb, p, pinv);
@@ -261,6 +282,10 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
   __syncthreads();
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
+  if (A.stagger_cycles > 0) {
+    const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
+    while (clock64() - t0 < wait) __nanosleep(256);
+  }
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
@@ -718,6 +743,7 @@ extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const u
   GateArgs A; memset(&A, 0, sizeof A);
   A.lwe1 = d_lwe1; A.lwe2 = d_lwe2; A.draws = d_draws; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor;
   A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL;
+  if (const char* sc = getenv("SGFHE_STAGGER")) { A.stagger_cycles = atoi(sc); A.stagger_slots = getenv("SGFHE_STAGGER_SLOTS") ? atoi(getenv("SGFHE_STAGGER_SLOTS")) : 16; }
   if (getenv("SGFHE_PHASE_TIMING")) {            // profiling aid: per-phase cycles of CTA 0, printed to stderr
     unsigned long long* d_t = nullptr; unsigned long long h_t[8] = {0};
     CK(cudaMalloc(&d_t, sizeof h_t)); CK(cudaMemset(d_t, 0, sizeof h_t));
