@@ -141,6 +141,9 @@ struct Shape {
   static constexpr int T = (M / 2 > 1024) ? 1024 : M / 2;
   static constexpr int NG = T / G;
   static constexpr int STR = M >> REM;       // stride of the fused top stages
+  // RNS basis sizes implied by Params(n), m = 8n (checked against the host derivation in sgfhe_ctx_create)
+  static constexpr int L = LOGM <= 10 ? 4 : 5;                        // bootstrap external product
+  static constexpr int LM = LOGM <= 10 ? 5 : (LOGM <= 12 ? 6 : 7);    // product of two full-size operands
 };
 
 // One radix-8 pass (active bits [B, B+3)) over NPOLY polynomials in shared memory.
@@ -313,19 +316,17 @@ __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c
 }
 
 // CRT lift: residues y_i = z (P/p_i)^-1 mod p_i of an integer |z| < P/32  ->  z mod Q, canonical.
-template <int BASIS>
-__device__ __forceinline__ u96 crt_lift(const DevConst& C, int K, const uint32_t* __restrict__ y, size_t stride) {
+template <int BASIS, int K>
+__device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __restrict__ y, size_t stride) {
   uint64_t colA[3] = {0, 0, 0}, colB[3] = {0, 0, 0}, vs = 0;
 #pragma unroll
-  for (int i = 0; i < MAXP; ++i) {
-    if (i < K) {
-      const uint32_t yi = y[i * stride];
-      vs += __umulhi(yi, C.vinv[i]);
+  for (int i = 0; i < K; ++i) {
+    const uint32_t yi = y[i * stride];
+    vs += __umulhi(yi, C.vinv[i]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (i < 4) colA[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
-        else colB[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
-      }
+    for (int k = 0; k < 3; ++k) {
+      if (i < 4) colA[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
+      else colB[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
     }
   }
   const uint32_t v = (uint32_t)((vs + (1u << 28)) >> 29);   // round(sum y_i / p_i)

@@ -89,10 +89,11 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
   using SH = Shape<LOGM>;
   long long tprev = timing ? clock64() : 0;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
-  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T, L = SH::L;
   const int tid = threadIdx.x;
   // Phase B: per RNS prime -- 4 forward NTTs, 8 MACs against the key tile, 2 inverse NTTs
-  for (int i = 0; i < C.L; ++i) {
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {
     const uint32_t p = C.p[i], p2 = 2 * p;
     if (tid == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);      // TMA: forward twiddles of this prime
     {
@@ -194,19 +195,19 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
   for (int c = 0; c < 2; ++c) {
     {
       const uint32_t* zr = S.zres + (size_t)c * m;
-      uint32_t yn[MAXP];                                 // next index's residues in flight
+      uint32_t yn[L];                                    // next index's residues in flight
 #pragma unroll
-      for (int i = 0; i < MAXP; ++i) yn[i] = i < C.L ? zr[(size_t)i * 2 * m + tid] : 0;
+      for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + tid];
 #pragma unroll 1
       for (int idx = tid; idx < m; idx += T) {
-        uint32_t yc[MAXP];
+        uint32_t yc[L];
 #pragma unroll
-        for (int i = 0; i < MAXP; ++i) yc[i] = yn[i];
+        for (int i = 0; i < L; ++i) yc[i] = yn[i];
         if (idx + T < m) {
 #pragma unroll
-          for (int i = 0; i < MAXP; ++i) if (i < C.L) yn[i] = zr[(size_t)i * 2 * m + idx + T];
+          for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + idx + T];
         }
-        st96(sm, m, idx, crt_lift<0>(C, C.L, yc, 1));
+        st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
       }
     }
     __syncthreads();
@@ -224,8 +225,10 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
       } else {
         const int src = (j - u) & (2 * m - 1);
         u96 zr = ld96(sm, m, src & (m - 1));
-        if (src >= m) zr = negmod96(zr, Q);
-        res = addmod96(a, submod96(zr, z, Q), Q);
+        uint32_t bw;
+        zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
+        res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
+        res = csubQ(csubQ(res, Q), Q);
       }
       st96(acc, m, j, res);
       if (decompose_next) {
@@ -371,14 +374,15 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
   extern __shared__ __align__(16) uint32_t sm[];
   using SH = Shape<LOGM>;
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
-  uint32_t* zres = scratch + (size_t)blockIdx.x * C.LM * m;
+  uint32_t* zres = scratch + (size_t)blockIdx.x * SH::LM * m;
   uint2* tab = reinterpret_cast<uint2*>(sm + 2 * m);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 4 * m);
   uint32_t parity = 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
   for (int g = blockIdx.x; g < batch; g += gridDim.x) {
-    for (int i = 0; i < C.LM; ++i) {
+#pragma unroll 1
+    for (int i = 0; i < SH::LM; ++i) {
       const uint32_t p = C.p[i], p2 = 2 * p;
       if (threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
       uint2 wt[R > 1 ? R - 1 : 1];
@@ -421,7 +425,7 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
       __syncthreads();
     }
     for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-      const u96 z = crt_lift<1>(C, C.LM, zres + idx, (size_t)m);
+      const u96 z = crt_lift<1, SH::LM>(C, zres + idx, (size_t)m);
       out[((size_t)g * m + idx) * 2] = (uint64_t)z.x0 | ((uint64_t)z.x1 << 32); out[((size_t)g * m + idx) * 2 + 1] = z.x2;
     }
     __syncthreads();
@@ -629,6 +633,11 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   c->smem_bytes = (size_t)24 * m + 16;                       // 4 NTT buffers + staged twiddle table + mbarrier
   int occ = 0;
   CK(configure_kernels(c, &occ));
+  {
+    int wantL = 0, wantLM = 0;
+    SGFHE_DISPATCH(hp.logm, { wantL = Shape<LOGM_>::L; wantLM = Shape<LOGM_>::LM; });
+    if (wantL != c->dc.L || wantLM != c->dc.LM) { delete c; return fail(SGFHE_ERR_MODULUS, "compiled RNS basis size does not match Params"); }
+  }
   if (occ < 1) { delete c; return fail(SGFHE_ERR_CUDA, "bootstrap kernel does not fit on an SM"); }
   c->max_ctas = occ * c->num_sms;
   c->scratch_stride = (scratch_bytes(m, c->dc.L) + 255) & ~(size_t)255;
