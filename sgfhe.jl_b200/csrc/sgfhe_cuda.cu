@@ -79,6 +79,70 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
   }
 }
 
+// Phase C/D per accumulator polynomial: CRT lift into shared memory, then acc += x^u z - z
+// (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product) fused with the next step's decomposition.
+template <int LOGM, int T>
+__device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
+                                           const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
+                                           unsigned long long* timing, long long& tprev) {
+  constexpr int m = 1 << LOGM, L = Shape<LOGM>::L;
+  const int tid = threadIdx.x;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+  const u96 Q = Q96(C);
+  for (int c = 0; c < 2; ++c) {
+    {
+      const uint32_t* zr = S.zres + (size_t)c * m;
+      uint32_t yn[L];                                    // next index's residues in flight
+#pragma unroll
+      for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + tid];
+#pragma unroll (T <= 512 ? 2 : 1)
+      for (int idx = tid; idx < m; idx += T) {
+        uint32_t yc[L];
+#pragma unroll
+        for (int i = 0; i < L; ++i) yc[i] = yn[i];
+        if (idx + T < m) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + idx + T];
+        }
+        st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
+      }
+    }
+    __syncthreads();
+    SGFHE_TICK(5);
+    uint32_t* acc = S.acc + c * 3 * m;
+    u96 an = ld96(acc, m, tid);                          // next index's accumulator limbs in flight
+#pragma unroll (T <= 512 ? 2 : 1)
+    for (int j = tid; j < m; j += T) {
+      const u96 a = an;
+      if (j + T < m) an = ld96(acc, m, j + T);
+      const u96 z = ld96(sm, m, j);
+      u96 res;
+      if (ext) {
+        res = z;
+      } else {
+        const int src = (j - u) & (2 * m - 1);
+        u96 zr = ld96(sm, m, src & (m - 1));
+        uint32_t bw;
+        zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
+        res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
+        res = csubQ(csubQ(res, Q), Q);
+      }
+      st96(acc, m, j, res);
+      if (decompose_next) {
+        int64_t d0, d1;
+        if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
+        else decompose_det(C, res, Q, d0, d1);
+        uint32_t lo, hi;
+        digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
+        digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
+      }
+    }
+    __syncthreads();
+    SGFHE_TICK(6);
+  }
+#undef SGFHE_TICK
+}
+
 // One accumulation step (body of src/fhe.jl:579-582) on digits already in S.dig; leaves the new accumulator in
 // S.acc and its decomposition (with `draws_next`, the following step's draws) in S.dig.  u = rotation in [0, 2m).
 template <int LOGM>
@@ -189,60 +253,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     __syncthreads();
     SGFHE_TICK(4);
   }
-  // Phase C/D per accumulator polynomial: CRT lift into shared memory, then acc += x^u z - z
-  // (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product) and the next step's decomposition.
-  const u96 Q = Q96(C);
-  for (int c = 0; c < 2; ++c) {
-    {
-      const uint32_t* zr = S.zres + (size_t)c * m;
-      uint32_t yn[L];                                    // next index's residues in flight
-#pragma unroll
-      for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + tid];
-#pragma unroll 1
-      for (int idx = tid; idx < m; idx += T) {
-        uint32_t yc[L];
-#pragma unroll
-        for (int i = 0; i < L; ++i) yc[i] = yn[i];
-        if (idx + T < m) {
-#pragma unroll
-          for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + idx + T];
-        }
-        st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
-      }
-    }
-    __syncthreads();
-    SGFHE_TICK(5);
-    uint32_t* acc = S.acc + c * 3 * m;
-    u96 an = ld96(acc, m, tid);                          // next index's accumulator limbs in flight
-#pragma unroll 1
-    for (int j = tid; j < m; j += T) {
-      const u96 a = an;
-      if (j + T < m) an = ld96(acc, m, j + T);
-      const u96 z = ld96(sm, m, j);
-      u96 res;
-      if (ext) {
-        res = z;
-      } else {
-        const int src = (j - u) & (2 * m - 1);
-        u96 zr = ld96(sm, m, src & (m - 1));
-        uint32_t bw;
-        zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
-        res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
-        res = csubQ(csubQ(res, Q), Q);
-      }
-      st96(acc, m, j, res);
-      if (decompose_next) {
-        int64_t d0, d1;
-        if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
-        else decompose_det(C, res, Q, d0, d1);
-        uint32_t lo, hi;
-        digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
-        digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
-      }
-    }
-    __syncthreads();
-    SGFHE_TICK(6);
-  }
+  crt_update<LOGM, T>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
 
@@ -320,6 +331,272 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
     }
     __syncthreads();
   }
+}
+
+
+// =========================================================================================================
+// v4: fused-pass step for m >= 4096 (512 threads, up to 128 registers per thread).
+//   * the digit load runs the top 3+REM stages in registers (radix 8/16) before the first store to shared memory;
+//   * the stride-1 forward pass, the 8 key MACs per point and the stride-1 inverse pass are one phase, so the
+//     key tile streams from L2 underneath butterflies instead of in a phase of its own;
+//   * the last inverse pass runs the top stages in registers and stores CRT-ready residues straight to HBM/L2;
+//   * only the FORWARD twiddle table is staged (TMA, one prime ahead): psi^-bitrev(2^l+g) = -psi^bitrev(2^l+(g^(2^l-1))),
+//     so every inverse twiddle is the negation of a mirrored forward entry.
+// =========================================================================================================
+template <int LOGM>
+struct Shape4 {
+  static constexpr int M = 1 << LOGM;
+  static constexpr int REM = LOGM % 3;            // 0 or 1 supported
+  static constexpr int LR0 = 3 + REM, R0 = 1 << LR0;
+  static constexpr int T = M >> LR0;              // 512 threads: one top-stage block per thread and polynomial
+  static constexpr int NB = (M / 8) / T;          // radix-8 blocks per thread and polynomial (1 or 2)
+  static constexpr int L = Shape<LOGM>::L;
+};
+
+__device__ __forceinline__ uint2 tw_neg(uint2 w, uint32_t p) { return make_uint2(p - w.x, ~w.y); }
+
+// twiddles of one radix-8 block from the staged forward table; inverse ones are mirrored and negated
+template <bool FWD>
+__device__ __forceinline__ void block_twiddles(const uint2* tab, int lvl, int g, uint32_t p, uint2 (&w)[7]) {
+  const int t1 = lvl + (FWD ? g : (g ^ (lvl - 1)));
+  const uint2 w0 = tab[t1];
+  const uint4 a = *reinterpret_cast<const uint4*>(&tab[2 * t1]);
+  const uint4 b0 = *reinterpret_cast<const uint4*>(&tab[4 * t1]);
+  const uint4 b1 = *reinterpret_cast<const uint4*>(&tab[4 * t1 + 2]);
+  if (FWD) {
+    w[0] = w0; w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
+    w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w); w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
+  } else {
+    w[0] = tw_neg(w0, p); w[1] = tw_neg(make_uint2(a.z, a.w), p); w[2] = tw_neg(make_uint2(a.x, a.y), p);
+    w[3] = tw_neg(make_uint2(b1.z, b1.w), p); w[4] = tw_neg(make_uint2(b1.x, b1.y), p);
+    w[5] = tw_neg(make_uint2(b0.z, b0.w), p); w[6] = tw_neg(make_uint2(b0.x, b0.y), p);
+  }
+}
+
+template <int LOGM, int NPOLY, bool FWD, int B>
+__device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_t p, uint32_t z) {
+  using S4 = Shape4<LOGM>;
+  constexpr int M = S4::M;
+  const uint32_t p2 = 2 * p;
+#pragma unroll
+  for (int q = 0; q < S4::NB; ++q) {
+    const int blk = threadIdx.x + q * S4::T;
+    const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
+    uint2 w[7];
+    block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = swz(base + (j << B));
+#pragma unroll
+    for (int poly = 0; poly < NPOLY; ++poly) {
+      uint32_t* s = sm + poly * M;
+      uint32_t x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = s[off[j]];
+      if (FWD) fwd_block<3>(x, w, p, p2, z); else inv_block<3>(x, w, p, p2, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[off[j]] = x[j];
+    }
+  }
+}
+
+// uniform top-stage twiddles of one prime into shared memory: fwd[k-1] = tw[k], inv[k-1] derived, k in [1, R0)
+template <int R0>
+__device__ __forceinline__ void write_top_twiddles(uint2* slot, const uint2* __restrict__ gtw, uint32_t p) {
+  const int k = threadIdx.x;
+  if (k >= 1 && k < R0) {
+    slot[k - 1] = __ldg(&gtw[k]);
+    const int lvl = 1 << (31 - __clz(k));
+    slot[R0 + k - 1] = tw_neg(__ldg(&gtw[lvl + ((k - lvl) ^ (lvl - 1))]), p);
+  }
+}
+
+template <int LOGM>
+__device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
+                             const uint2* __restrict__ tw_f, const int64_t* __restrict__ draws_next, int u, bool ext,
+                             bool decompose_next, uint2* tab, uint64_t* bar, uint2* toptw, uint32_t& parity, uint32_t& pc,
+                             unsigned long long* timing) {
+  using S4 = Shape4<LOGM>;
+  constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, L = S4::L;
+  const int tid = threadIdx.x;
+  long long tprev = timing ? clock64() : 0;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+#pragma unroll 1
+  for (int i = 0; i < L; ++i, ++pc) {
+    const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
+    const uint2* top = toptw + (pc & 1) * 2 * R0;        // [0,R0): forward, [R0,2R0): inverse top-stage twiddles
+    // ---- P0: digits -> residues -> top LR0 stages in registers -> shared memory (register double buffered) ----
+    {
+      const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
+      uint32_t lo[2][R0], hi[2][R0];
+#pragma unroll
+      for (int k = 0; k < R0; ++k) { lo[0][k] = S.diglo[tid + k * T]; hi[0][k] = S.dighi[tid + k * T]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j + 1 < 4) {
+#pragma unroll
+          for (int k = 0; k < R0; ++k) { lo[(j + 1) & 1][k] = S.diglo[(j + 1) * m + tid + k * T]; hi[(j + 1) & 1][k] = S.dighi[(j + 1) * m + tid + k * T]; }
+        }
+        uint32_t x[R0];
+#pragma unroll
+        for (int k = 0; k < R0; ++k) x[k] = digit_mod(lo[j & 1][k], hi[j & 1][k], mu, negc, p);
+        fwd_block<LR0>(x, top, p, p2, z);
+#pragma unroll
+        for (int k = 0; k < R0; ++k) sm[j * m + swz(tid + k * T)] = x[k];
+      }
+    }
+    __syncthreads();
+    mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
+    SGFHE_TICK(0);
+    pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
+    __syncthreads();
+    pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
+    __syncwarp();                                        // bits [0,6) stay inside groups of 8 consecutive threads
+    SGFHE_TICK(1);
+    // ---- fused: stride-1 forward pass + 8 key MACs per point + stride-1 inverse pass ------------------------
+    {
+      const uint32_t* K = keyrow + (size_t)i * 8 * m;    // [4][2][m] for this prime   (src/fhe.jl:527-528)
+      const uint32_t pinv = C.pinv_neg[i];
+      uint4 kq[2][4];                                    // key words of (block, poly): rows 2j and 2j+1, 8 indices each
+      {
+        const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * tid);
+        kq[0][0] = __ldg(k0); kq[0][1] = __ldg(k0 + 1);
+        const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * tid);
+        kq[0][2] = __ldg(k1); kq[0][3] = __ldg(k1 + 1);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int blk = tid + q * T, base = 8 * blk;
+        const int a0 = swz(base), a1 = a0 ^ 4;
+        uint2 w[7];
+        block_twiddles<true>(tab, m / 8, blk, p, w);
+        uint64_t sa[8], sb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sa[e] = 0; sb[e] = 0; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int sidx = q * 4 + j;
+          if (sidx + 1 < NB * 4) {                       // prefetch the next (block, poly) key words
+            const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
+            const uint4* k0 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj) * m + 8 * (tid + nq * T));
+            const uint4* k1 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj + 1) * m + 8 * (tid + nq * T));
+            kq[(sidx + 1) & 1][0] = __ldg(k0); kq[(sidx + 1) & 1][1] = __ldg(k0 + 1);
+            kq[(sidx + 1) & 1][2] = __ldg(k1); kq[(sidx + 1) & 1][3] = __ldg(k1 + 1);
+          }
+          uint32_t x[8];
+          {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(sm + j * m + a0);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(sm + j * m + a1);
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+          }
+          fwd_block<3>(x, w, p, p2, z);
+          const uint4* kk = kq[sidx & 1];
+          const uint32_t ka[8] = {kk[0].x, kk[0].y, kk[0].z, kk[0].w, kk[1].x, kk[1].y, kk[1].z, kk[1].w};
+          const uint32_t kb[8] = {kk[2].x, kk[2].y, kk[2].z, kk[2].w, kk[3].x, kk[3].y, kk[3].z, kk[3].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            uint32_t d = x[e];
+            d = min(d, d - p2); d = min(d, d - p);
+            sa[e] += (uint64_t)d * ka[e];
+            sb[e] += (uint64_t)d * kb[e];
+          }
+        }
+        uint2 wi[7];
+        block_twiddles<false>(tab, m / 8, blk, p, wi);
+        uint32_t ya[8], yb[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ya[e] = redc(sa[e], p, pinv); yb[e] = redc(sb[e], p, pinv); }
+        inv_block<3>(ya, wi, p, p2, z);
+        inv_block<3>(yb, wi, p, p2, z);
+        *reinterpret_cast<uint4*>(sm + a0) = make_uint4(ya[0], ya[1], ya[2], ya[3]);
+        *reinterpret_cast<uint4*>(sm + a1) = make_uint4(ya[4], ya[5], ya[6], ya[7]);
+        *reinterpret_cast<uint4*>(sm + m + a0) = make_uint4(yb[0], yb[1], yb[2], yb[3]);
+        *reinterpret_cast<uint4*>(sm + m + a1) = make_uint4(yb[4], yb[5], yb[6], yb[7]);
+      }
+    }
+    __syncwarp();
+    SGFHE_TICK(2);
+    pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
+    __syncthreads();
+    pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
+    __syncthreads();                                     // last reader of `tab` for this prime is done
+    {
+      const int nxt = (i + 1 == L) ? 0 : i + 1;          // TMA: next prime's forward table under the store phase
+      if (tid == 0) stage_table(tab, tw_f + (size_t)nxt * m, m * 8, bar);
+      write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
+    }
+    SGFHE_TICK(3);
+    // ---- top inverse stages in registers + CRT pre-scaling + store of the residues --------------------------
+    {
+      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t x[R0];
+#pragma unroll
+        for (int k = 0; k < R0; ++k) x[k] = sm[c * m + swz(tid + k * T)];
+        inv_block<LR0>(x, top + R0, p, p2, z);
+#pragma unroll
+        for (int k = 0; k < R0; ++k) S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(x[k], sc, scs, p), p);
+      }
+    }
+    __syncthreads();
+    SGFHE_TICK(4);
+  }
+  crt_update<LOGM, T>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
+#undef SGFHE_TICK
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
+bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  using S4 = Shape4<LOGM>;
+  constexpr int m = 1 << LOGM;
+  const int n = C.n;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint2* toptw = reinterpret_cast<uint2*>(sm + 6 * m + 4);           // [2 slots][fwd R0 | inv R0]
+  uint32_t parity = 0, pc = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage_table(tab, A.tw_f, m * 8, bar);
+  }
+  write_top_twiddles<S4::R0>(toptw, A.tw_f, C.p[0]);
+  __syncthreads();
+  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
+  const uint64_t rmask = (1ull << C.logr) - 1;
+  for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
+    const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
+    const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
+    const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
+    if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
+    __syncthreads();
+    if ((A.flags & F_DECOMP) && A.step_begin < A.step_end) {
+      decompose_poly<LOGM>(C, S, 0, dr);
+      decompose_poly<LOGM>(C, S, 1, dr);
+    }
+    __syncthreads();
+    for (int k = A.step_begin; k < A.step_end; ++k) {
+      const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
+      const bool more = k + 1 < A.step_end;
+      gate_step_v4<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f,
+                         (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
+                         tab, bar, toptw, parity, pc, blockIdx.x == 0 ? A.timing : nullptr);
+    }
+    if (A.trace) {
+      for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
+        const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
+        A.trace[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); A.trace[2 * e + 1] = v.x2;
+      }
+    }
+    if (A.flags & F_FINAL) {
+      const size_t w = (A.flags & F_RAW) ? 2 : 1;
+      gate_final(C, S, A.out_and + (size_t)g * (n + 1) * w, A.out_or + (size_t)g * (n + 1) * w,
+                 A.out_xor + (size_t)g * (n + 1) * w, (A.flags & F_RAW) != 0);
+    }
+    __syncthreads();
+  }
+  mbar_wait(bar, parity);                                // the table staged for a step that never runs
 }
 
 // Key pre-transform (K10): coefficient-form wide polys -> per-prime NTT domain, Montgomery form.
@@ -468,7 +745,8 @@ struct sgfhe_ctx {
   int device = 0;
   HostParams hp;
   DevConst dc;
-  int num_sms = 0, threads = 0, max_ctas = 0;
+  int num_sms = 0, threads = 0, boot_threads = 0, max_ctas = 0;
+  bool use_v4 = false;
   size_t smem_bytes = 0, scratch_stride = 0;
   uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
   uint32_t* d_keyhat = nullptr; int key_rows = 0; size_t keyhat_capacity_rows = 0;
@@ -562,19 +840,39 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     default: { constexpr int LOGM_ = 13; STMT; } break;    \
   }
 
+#define SGFHE_DISPATCH_V4(logm, STMT)                      \
+  switch (logm) {                                          \
+    case 12: { constexpr int LOGM_ = 12; STMT; } break;    \
+    default: { constexpr int LOGM_ = 13; STMT; } break;    \
+  }
+
 static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   cudaError_t e = cudaSuccess;
+  c->use_v4 = c->hp.logm >= 12 && !getenv("SGFHE_FORCE_V3");
+  if (c->use_v4) {
+    SGFHE_DISPATCH_V4(c->hp.logm, {
+      c->boot_threads = Shape4<LOGM_>::T;
+      e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_>, c->boot_threads, c->smem_bytes);
+    });
+    if (e != cudaSuccess) return e;
+  }
   SGFHE_DISPATCH(c->hp.logm, {
     c->threads = Shape<LOGM_>::T;
+    if (!c->use_v4) c->boot_threads = c->threads;
     e = cudaFuncSetAttribute(bootstrap_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(key_transform_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(polymul_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel<LOGM_>, c->threads, c->smem_bytes);
+    if (e == cudaSuccess && !c->use_v4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel<LOGM_>, c->threads, c->smem_bytes);
   });
   return e;
 }
 static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, const GateArgs& A) {
-  SGFHE_DISPATCH(c->hp.logm, (bootstrap_kernel<LOGM_><<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A)));
+  if (c->use_v4) {
+    SGFHE_DISPATCH_V4(c->hp.logm, (bootstrap_kernel_v4<LOGM_><<<grid, c->boot_threads, c->smem_bytes, st>>>(c->dc, A)));
+  } else {
+    SGFHE_DISPATCH(c->hp.logm, (bootstrap_kernel<LOGM_><<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A)));
+  }
   ++g_launches;
 }
 static void launch_key_transform(const sgfhe_ctx* c, int npolys, const uint64_t* d_coef, uint32_t* d_keyhat, int poly0) {
@@ -630,7 +928,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   const int m = hp.m;
-  c->smem_bytes = (size_t)24 * m + 16;                       // 4 NTT buffers + staged twiddle table + mbarrier
+  c->smem_bytes = (size_t)24 * m + 16 + 1024;                // 4 NTT buffers + staged twiddle table + mbarrier + top-stage twiddles
   int occ = 0;
   CK(configure_kernels(c, &occ));
   {
