@@ -89,52 +89,66 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   const u96 Q = Q96(C);
+  // Both loops read data written a whole step ago (largely evicted to HBM): keep D iterations of loads in flight.
+  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
   for (int c = 0; c < 2; ++c) {
     {
       const uint32_t* zr = S.zres + (size_t)c * m;
-      uint32_t yn[L];                                    // next index's residues in flight
+      uint32_t yq[D][L];
 #pragma unroll
-      for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + tid];
-#pragma unroll (T <= 512 ? 2 : 1)
-      for (int idx = tid; idx < m; idx += T) {
-        uint32_t yc[L];
+      for (int d = 0; d < D; ++d)
 #pragma unroll
-        for (int i = 0; i < L; ++i) yc[i] = yn[i];
-        if (idx + T < m) {
+        for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + tid + d * T];
+#pragma unroll 1
+      for (int it0 = 0; it0 < NIT; it0 += D) {
 #pragma unroll
-          for (int i = 0; i < L; ++i) yn[i] = zr[(size_t)i * 2 * m + idx + T];
+        for (int d = 0; d < D; ++d) {
+          const int idx = tid + (it0 + d) * T;
+          uint32_t yc[L];
+#pragma unroll
+          for (int i = 0; i < L; ++i) yc[i] = yq[d][i];
+          if (it0 + d + D < NIT) {
+#pragma unroll
+            for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
+          }
+          st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
         }
-        st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
       }
     }
     __syncthreads();
     SGFHE_TICK(5);
     uint32_t* acc = S.acc + c * 3 * m;
-    u96 an = ld96(acc, m, tid);                          // next index's accumulator limbs in flight
-#pragma unroll (T <= 512 ? 2 : 1)
-    for (int j = tid; j < m; j += T) {
-      const u96 a = an;
-      if (j + T < m) an = ld96(acc, m, j + T);
-      const u96 z = ld96(sm, m, j);
-      u96 res;
-      if (ext) {
-        res = z;
-      } else {
-        const int src = (j - u) & (2 * m - 1);
-        u96 zr = ld96(sm, m, src & (m - 1));
-        uint32_t bw;
-        zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
-        res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
-        res = csubQ(csubQ(res, Q), Q);
-      }
-      st96(acc, m, j, res);
-      if (decompose_next) {
-        int64_t d0, d1;
-        if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
-        else decompose_det(C, res, Q, d0, d1);
-        uint32_t lo, hi;
-        digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
-        digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
+    u96 aq[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) aq[d] = ld96(acc, m, tid + d * T);
+#pragma unroll 1
+    for (int it0 = 0; it0 < NIT; it0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int j = tid + (it0 + d) * T;
+        const u96 a = aq[d];
+        if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
+        const u96 z = ld96(sm, m, j);
+        u96 res;
+        if (ext) {
+          res = z;
+        } else {
+          const int src = (j - u) & (2 * m - 1);
+          u96 zr = ld96(sm, m, src & (m - 1));
+          uint32_t bw;
+          zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
+          res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
+          res = csubQ(csubQ(res, Q), Q);
+        }
+        st96(acc, m, j, res);
+        if (decompose_next) {
+          int64_t d0, d1;
+          if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
+          else decompose_det(C, res, Q, d0, d1);
+          uint32_t lo, hi;
+          digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
+          digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
+        }
       }
     }
     __syncthreads();
