@@ -26,8 +26,9 @@ struct DevConst {
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
   uint64_t barrett_mu;          // floor(2^(sbits+35) / Q)
+  double barrett_inv;           // 2^(sbits-29) / Q, rounded down and scaled by (1 - 2^-40)
   uint32_t Ql[3], offl[3];      // Q and offs as 32-bit limbs
-  uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP];
+  uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP], vk[MAXP];
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
@@ -316,20 +317,24 @@ __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c
 }
 
 // CRT lift: residues y_i = z (P/p_i)^-1 mod p_i of an integer |z| < P/32  ->  z mod Q, canonical.
+//   v = round(sum y_i / p_i) from the top 14 bits of each residue (error < 2^-11, margin 0.47);
+//   S = sum y_i c_i + v negP  (< 2^126);  z = S mod Q by a Barrett step whose quotient estimate is one
+//   double-precision multiply (the fp64 and conversion pipes are otherwise idle; the integer pipe is the bottleneck).
 template <int BASIS, int K>
 __device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __restrict__ y, size_t stride) {
-  uint64_t colA[3] = {0, 0, 0}, colB[3] = {0, 0, 0}, vs = 0;
+  uint64_t colA[3] = {0, 0, 0}, colB[3] = {0, 0, 0};
+  uint32_t vs = 0;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     const uint32_t yi = y[i * stride];
-    vs += __umulhi(yi, C.vinv[i]);
+    vs += (yi >> 16) * C.vk[i];                               // vk = round(2^44 / p): (y>>16) vk ~ (y/p) 2^28
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (i < 4) colA[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
       else colB[k] += (uint64_t)yi * C.crt_c[BASIS][i][k];
     }
   }
-  const uint32_t v = (uint32_t)((vs + (1u << 28)) >> 29);   // round(sum y_i / p_i)
+  const uint32_t v = (vs + (1u << 27)) >> 28;                 // round(sum y_i / p_i), 0 <= v <= K
 #pragma unroll
   for (int k = 0; k < 3; ++k) colB[k] += (uint64_t)v * C.negP[BASIS][k];
   // S = sum_k (colA[k] + colB[k]) 2^(32k) < 2^126, as four limbs
@@ -345,10 +350,10 @@ __device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __res
     s2 = (uint32_t)t2;
     s3 = (uint32_t)((t2 >> 32) + (c2 >> 32) + k1);
   }
-  // Barrett: qh = floor(floor(S / 2^(sbits-29)) mu / 2^64) in [S/Q - 2, S/Q]
+  // quotient estimate qh in [S/Q - 3, S/Q]: T = floor(S / 2^(sbits-29)) < 2^63, qh = trunc(T * qinv), qinv ~ 2^(sbits-29)/Q biased down
   const int sh = C.sbits - 29 - 32;                           // 0 <= sh < 32
   const uint32_t tl = __funnelshift_r(s1, s2, sh), th = __funnelshift_r(s2, s3, sh);
-  const uint64_t qh = __umul64hi((uint64_t)tl | ((uint64_t)th << 32), C.barrett_mu);
+  const uint64_t qh = __double2ull_rz(__ull2double_rz((uint64_t)tl | ((uint64_t)th << 32)) * C.barrett_inv);
   const uint32_t q0 = (uint32_t)qh, q1 = (uint32_t)(qh >> 32);
   const uint64_t m0 = (uint64_t)q0 * C.Ql[0];
   const uint64_t m1 = (uint64_t)q0 * C.Ql[1] + (m0 >> 32);
@@ -358,7 +363,8 @@ __device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __res
   u96 S; S.x0 = s0; S.x1 = s1; S.x2 = s2;
   uint32_t bw;
   const u96 Q = Q96(C);
-  u96 R = sub96(S, prod, bw);                                 // exact mod 2^96; true value in [0, 3Q)
+  u96 R = sub96(S, prod, bw);                                 // exact mod 2^96; true value in [0, 4Q), 4Q < 2^96
+  R = csubQ(R, Q);
   R = csubQ(R, Q);
   R = csubQ(R, Q);
   return R;

@@ -9,6 +9,7 @@
 #include "host_math.h"
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -435,6 +436,12 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
   const int tid = threadIdx.x;
   long long tprev = timing ? clock64() : 0;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+  // Digit words are prime independent.  Polynomials are processed in the order 2,3,0,1: buffers 2,3 are not read
+  // by the previous prime's residue store, so that store overlaps the head of the next digit load.
+  const int st = swz(tid);                               // swz(tid + k T) = swz(tid) + k T  (T is a multiple of 256)
+  uint32_t dl[2][R0], dh[2][R0];
+#pragma unroll
+  for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
 #pragma unroll 1
   for (int i = 0; i < L; ++i, ++pc) {
     const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
@@ -442,21 +449,21 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     // ---- P0: digits -> residues -> top LR0 stages in registers -> shared memory (register double buffered) ----
     {
       const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
-      uint32_t lo[2][R0], hi[2][R0];
 #pragma unroll
-      for (int k = 0; k < R0; ++k) { lo[0][k] = S.diglo[tid + k * T]; hi[0][k] = S.dighi[tid + k * T]; }
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = (jj + 2) & 3;
+        if (jj + 1 < 4) {
+          const int jn = (jj + 3) & 3;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j + 1 < 4) {
-#pragma unroll
-          for (int k = 0; k < R0; ++k) { lo[(j + 1) & 1][k] = S.diglo[(j + 1) * m + tid + k * T]; hi[(j + 1) & 1][k] = S.dighi[(j + 1) * m + tid + k * T]; }
+          for (int k = 0; k < R0; ++k) { dl[(jj + 1) & 1][k] = S.diglo[jn * m + tid + k * T]; dh[(jj + 1) & 1][k] = S.dighi[jn * m + tid + k * T]; }
         }
+        if (jj == 2) __syncthreads();                    // previous prime's residue store has left buffers 0,1
         uint32_t x[R0];
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = digit_mod(lo[j & 1][k], hi[j & 1][k], mu, negc, p);
+        for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[jj & 1][k], dh[jj & 1][k], mu, negc, p);
         fwd_block<LR0>(x, top, p, p2, z);
 #pragma unroll
-        for (int k = 0; k < R0; ++k) sm[j * m + swz(tid + k * T)] = x[k];
+        for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
       }
     }
     __syncthreads();
@@ -464,20 +471,20 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     SGFHE_TICK(0);
     pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
     __syncthreads();
+    const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
+    uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
+    {                                                    // the first set is requested before the stride-8 pass
+      const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * tid);
+      kq[0][0] = __ldg(k0); kq[0][1] = __ldg(k0 + 1);
+      const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * tid);
+      kq[0][2] = __ldg(k1); kq[0][3] = __ldg(k1 + 1);
+    }
     pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
     __syncwarp();                                        // bits [0,6) stay inside groups of 8 consecutive threads
     SGFHE_TICK(1);
     // ---- fused: stride-1 forward pass + 8 key MACs per point + stride-1 inverse pass ------------------------
     {
-      const uint32_t* K = keyrow + (size_t)i * 8 * m;    // [4][2][m] for this prime   (src/fhe.jl:527-528)
       const uint32_t pinv = C.pinv_neg[i];
-      uint4 kq[2][4];                                    // key words of (block, poly): rows 2j and 2j+1, 8 indices each
-      {
-        const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * tid);
-        kq[0][0] = __ldg(k0); kq[0][1] = __ldg(k0 + 1);
-        const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * tid);
-        kq[0][2] = __ldg(k1); kq[0][3] = __ldg(k1 + 1);
-      }
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
         const int blk = tid + q * T, base = 8 * blk;
@@ -539,6 +546,10 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
       if (tid == 0) stage_table(tab, tw_f + (size_t)nxt * m, m * 8, bar);
       write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
     }
+    if (i + 1 < L) {                                     // next prime's first digit words, requested under the store phase
+#pragma unroll
+      for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+    }
     SGFHE_TICK(3);
     // ---- top inverse stages in registers + CRT pre-scaling + store of the residues --------------------------
     {
@@ -547,15 +558,15 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
       for (int c = 0; c < 2; ++c) {
         uint32_t x[R0];
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = sm[c * m + swz(tid + k * T)];
+        for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
         inv_block<LR0>(x, top + R0, p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0; ++k) S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(x[k], sc, scs, p), p);
       }
     }
-    __syncthreads();
     SGFHE_TICK(4);
   }
+  __syncthreads();                                       // residues stored, shared memory free for the CRT staging
   crt_update<LOGM, T>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
@@ -795,6 +806,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   dc->offs = h_mulmod(s, (1 + hp.B) % hp.Q, hp.Q);
   to_limbs(hp.Q, dc->Ql); to_limbs(dc->offs, dc->offl);
   dc->barrett_mu = (uint64_t)(((u128)1 << (dc->sbits + 35)) / hp.Q);
+  dc->barrett_inv = ldexp((double)dc->barrett_mu, -64) * (1.0 - ldexp(1.0, -40));
   const int NP = L > LM ? L : LM;
   for (int i = 0; i < NP; ++i) {
     const uint32_t p = primes[i];
@@ -803,6 +815,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     dc->pinv_neg[i] = 0u - inv;
     dc->dig_mu[i] = (uint32_t)(((uint64_t)1 << 50) / p);
     dc->vinv[i] = (uint32_t)(((uint64_t)1 << 61) / p);
+    dc->vk[i] = (uint32_t)((((uint64_t)1 << 44) + p / 2) / p);
     dc->r32[i] = (uint32_t)(((uint64_t)1 << 32) % p);
     dc->r64[i] = (uint32_t)((((u128)1) << 64) % p);
     dc->qmodp[i] = (uint32_t)(hp.Q % p);
