@@ -31,22 +31,24 @@ struct GateArgs {
   uint64_t* trace;                              // NULL or [2][m][2]: accumulator after the last step run
   const uint32_t* keyhat;                       // [rows][L][4][2][m] Montgomery form, NTT order
   const uint2* tw_f; const uint2* tw_i;         // [MAXP][m]
-  uint8_t* scratch; size_t scratch_stride;      // per CTA
+  uint8_t* scratch; size_t scratch_stride;      // per CTA: accumulator + digits (kept L2-persistent)
+  uint8_t* zres; size_t zres_stride;            // per CTA: inverse-transform residues
   int batch, step_begin, step_end, draw_steps, flags;
   unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
   int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
 
 struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; uint32_t* zres; };
-__device__ __forceinline__ Scratch carve(uint8_t* base, int m) {
+__device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   Scratch s;
   s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
   s.diglo = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);       // [4][m]
   s.dighi = reinterpret_cast<uint32_t*>(base + (size_t)40 * m);       // [4][m]
-  s.zres = reinterpret_cast<uint32_t*>(base + (size_t)56 * m);        // [L][2][m]
+  s.zres = reinterpret_cast<uint32_t*>(zbase);                        // [L][2][m]
   return s;
 }
-static size_t scratch_bytes(int m, int L) { return (size_t)(56 + 8 * L) * m; }
+static size_t scratch_bytes(int m) { return (size_t)56 * m; }
+static size_t zres_bytes(int m, int L) { return (size_t)8 * L * m; }
 
 // accumulator init: a = 0, b = t(x) x^(-u_b) DQ   (src/fhe.jl:566-573, t(x) from src/fhe.jl:535-548)
 template <int LOGM>
@@ -92,6 +94,9 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   const u96 Q = Q96(C);
   // Both loops read data written a whole step ago (largely evicted to HBM): keep D iterations of loads in flight.
   constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
+  // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT lift runs
+  for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
   for (int c = 0; c < 2; ++c) {
     {
       const uint32_t* zr = S.zres + (size_t)c * m;
@@ -309,7 +314,7 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
   uint32_t parity = 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
+  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
   if (A.stagger_cycles > 0) {
     const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
@@ -588,7 +593,7 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
   }
   write_top_twiddles<S4::R0>(toptw, A.tw_f, C.p[0]);
   __syncthreads();
-  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, m);
+  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
@@ -772,7 +777,8 @@ struct sgfhe_ctx {
   DevConst dc;
   int num_sms = 0, threads = 0, boot_threads = 0, max_ctas = 0;
   bool use_v4 = false;
-  size_t smem_bytes = 0, scratch_stride = 0;
+  size_t smem_bytes = 0, scratch_stride = 0, zres_stride = 0;
+  int persist_l2 = 0;                              // pin accumulator + digit scratch in L2 (access policy window)
   uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
   uint32_t* d_keyhat = nullptr; int key_rows = 0; size_t keyhat_capacity_rows = 0;
   uint8_t* d_scratch = nullptr; int scratch_ctas = 0;
@@ -896,7 +902,20 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
 }
 static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, const GateArgs& A) {
   if (c->use_v4) {
-    SGFHE_DISPATCH_V4(c->hp.logm, (bootstrap_kernel_v4<LOGM_><<<grid, c->boot_threads, c->smem_bytes, st>>>(c->dc, A)));
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1]; int nattr = 0;
+    if (c->persist_l2) {                               // accumulator + digits of the resident CTAs stay in L2 across steps
+      attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[0].val.accessPolicyWindow.base_ptr = A.scratch;
+      attr[0].val.accessPolicyWindow.num_bytes = (size_t)grid * A.scratch_stride;
+      attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+      attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      nattr = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    SGFHE_DISPATCH_V4(c->hp.logm, (cudaLaunchKernelEx(&cfg, bootstrap_kernel_v4<LOGM_>, c->dc, A)));
   } else {
     SGFHE_DISPATCH(c->hp.logm, (bootstrap_kernel<LOGM_><<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A)));
   }
@@ -954,6 +973,10 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
+  if (getenv("SGFHE_L2_PERSIST")) {
+    fprintf(stderr, "[sgfhe] L2 %d MB, persisting max %d MB, window max %d MB\n", prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
+  }
   const int m = hp.m;
   c->smem_bytes = (size_t)24 * m + 16 + 1024;                // 4 NTT buffers + staged twiddle table + mbarrier + top-stage twiddles
   int occ = 0;
@@ -965,7 +988,9 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   }
   if (occ < 1) { delete c; return fail(SGFHE_ERR_CUDA, "bootstrap kernel does not fit on an SM"); }
   c->max_ctas = occ * c->num_sms;
-  c->scratch_stride = (scratch_bytes(m, c->dc.L) + 255) & ~(size_t)255;
+  c->scratch_stride = (scratch_bytes(m) + 255) & ~(size_t)255;
+  c->zres_stride = (zres_bytes(m, c->dc.L) + 255) & ~(size_t)255;
+  c->persist_l2 = getenv("SGFHE_L2_PERSIST") ? atoi(getenv("SGFHE_L2_PERSIST")) : 0;
   CK(cudaMalloc(&c->d_tw_f, twf.size() * sizeof(uint2)));
   CK(cudaMalloc(&c->d_tw_i, twi.size() * sizeof(uint2)));
   CK(cudaMemcpy(c->d_tw_f, twf.data(), twf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
@@ -1002,7 +1027,7 @@ static int ensure_keyhat(sgfhe_ctx* c, int rows) {
 static int ensure_scratch(sgfhe_ctx* c, int ctas) {
   if (ctas <= c->scratch_ctas) return SGFHE_OK;
   if (c->d_scratch) { cudaFree(c->d_scratch); c->d_scratch = nullptr; c->scratch_ctas = 0; }
-  if (cudaMalloc(&c->d_scratch, (size_t)ctas * c->scratch_stride) != cudaSuccess)
+  if (cudaMalloc(&c->d_scratch, (size_t)ctas * (c->scratch_stride + c->zres_stride)) != cudaSuccess)
     return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the gate scratch failed");
   c->scratch_ctas = ctas;
   return SGFHE_OK;
@@ -1061,6 +1086,7 @@ static int launch_gates(sgfhe_ctx* c, GateArgs& A, cudaStream_t st) {
   int rc = ensure_scratch(c, grid); if (rc) return rc;
   A.keyhat = c->d_keyhat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i;
   A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
+  A.zres = c->d_scratch + (size_t)c->scratch_ctas * c->scratch_stride; A.zres_stride = c->zres_stride;
   launch_bootstrap(c, grid, st, A);
   CK(cudaGetLastError());
   return SGFHE_OK;
@@ -1250,6 +1276,7 @@ extern "C" int sgfhe_external_product(sgfhe_ctx* c, const uint64_t* a, const uin
       A.draws = d_draws; A.flags = F_EXT | F_DECOMP; A.trace = d_ab;
       A.out_and = A.out_or = A.out_xor = dummy;
       A.keyhat = d_khat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i; A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
+      A.zres = c->d_scratch + (size_t)c->scratch_ctas * c->scratch_stride; A.zres_stride = c->zres_stride;
       launch_bootstrap(c, 1, nullptr, A);
       e = cudaGetLastError();
     }
