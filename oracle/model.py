@@ -257,3 +257,31 @@ def decrypt_lwe(P: Params, sk, lwe) -> int:
     """fhe.jl:504-507"""
     b1 = (int(lwe[P.n]) - sum(int(x) for x, s in zip(lwe, sk) if s)) % P.r
     return ((b1 + P.Dr // 2) % P.r) // P.Dr
+
+
+def shortened_external_product(a, A, B, Q, draws=None):
+    """fhe.jl:632-641.  A[j][c]; uses rows l+1..2l (0-based 2, 3); draws [N][2] or None."""
+    u = flatten_poly(a, B, 2, Q, draws)
+    N = len(a)
+    res = []
+    for c in range(2):
+        acc = [0] * N
+        for j in range(2):
+            acc = [(x + y) % Q for x, y in zip(acc, polymul(u[j], A[2 + j][c], Q))]
+        res.append(acc)
+    return res[0], res[1]
+
+
+def pack_from_lwes(P: Params, key, new_lwes, draws_short=None):
+    """fhe.jl:675-693 given new_lwes[j] = (a..., b) over Z_Q; key[i][j][c]; returns (w, v) over Z_r, length m."""
+    n, m, Q = P.n, P.m, P.Q
+    w_t, v_t = [0] * m, [0] * m
+    for i in range(n):
+        as_i = [int(new_lwes[j][i]) for j in range(n)] + [0] * (m - n)          # fhe.jl:675-677
+        w, v = shortened_external_product(as_i, key[i], P.B, Q, None if draws_short is None else draws_short[i])
+        w_t = [(x + y) % Q for x, y in zip(w_t, w)]
+        v_t = [(x + y) % Q for x, y in zip(v_t, v)]
+    b = [int(new_lwes[j][n]) for j in range(n)] + [0] * (m - n)                 # fhe.jl:678
+    w1 = [(-x) % Q for x in w_t]                                                # fhe.jl:689
+    v1 = [(x - y) % Q for x, y in zip(b, v_t)]                                  # fhe.jl:690
+    return [rescale(P.r, x, Q, True) for x in w1], [rescale(P.r, x, Q, True) for x in v1]

@@ -684,3 +684,118 @@ void sgo_decrypt_packed(const sgo_params* P, const uint8_t* sk, const uint64_t* 
   for (int k = 0; k < n; ++k) bits_out[k] = ((((b[k] - ks[k]) & mask) + P->Dr / 2) & mask) / P->Dr;
   free(ks);
 }
+
+/* fhe.jl:632-641: flatten(a) * A[l+1:2l, :] -- rows 3,4 (1-based) of the 4x2 matrix.  draws [N][2] or NULL. */
+static void shortened_product_u(const ntt_plan* p, const u128* a, const u128* A, u128 B, const int64_t* draws,
+                                u128* a_out, u128* b_out, u128* work /* 4N */) {
+  int N = p->N; u128 Q = p->Q;
+  u128* u = work; u128* prod = work + 2 * (size_t)N; u128* tmp = work + 3 * (size_t)N;
+  flatten_poly_u(a, N, B, Q, draws, u, u + N);                 /* fhe.jl:637 */
+  for (int c = 0; c < 2; ++c) {
+    u128* res = c ? b_out : a_out;
+    for (int j = 0; j < 2; ++j) {                              /* fhe.jl:638-639 */
+      polymul_u(p, u + (size_t)j * N, A + ((size_t)(2 + j) * 2 + c) * N, prod, tmp);
+      if (j == 0) memcpy(res, prod, N * sizeof(u128));
+      else for (int k = 0; k < N; ++k) res[k] = addmod(res[k], prod[k], Q);
+    }
+  }
+}
+
+int sgo_shortened_external_product(const sgo_u128* a, const sgo_u128* A, int N, sgo_u128 Bs, sgo_u128 Qs,
+                                   const int64_t* draws, sgo_u128* a_out, sgo_u128* b_out) {
+  u128 Q = U(Qs); const ntt_plan* p = get_plan(N, Q); if (!p) return -1;
+  size_t n = N;
+  u128* buf = (u128*)malloc((1 + 8 + 2 + 4) * n * sizeof(u128));
+  u128 *ua = buf, *uA = buf + n, *oa = buf + 9 * n, *ob = buf + 10 * n, *work = buf + 11 * n;
+  for (size_t i = 0; i < n; ++i) ua[i] = U(a[i]);
+  for (size_t i = 0; i < 8 * n; ++i) uA[i] = U(A[i]);
+  shortened_product_u(p, ua, uA, U(Bs), draws, oa, ob, work);
+  for (size_t i = 0; i < n; ++i) { a_out[i] = S(oa[i]); b_out[i] = S(ob[i]); }
+  free(buf); return 0;
+}
+
+/* fhe.jl:675-693 given the n AND-outputs of _bootstrap_internal(bkey, rng, trivial(1), bit_j) over Z_Q
+ * (new_lwes [n][n+1] wide): transpose, n shortened products against bkey.key[i], sum, negate/subtract, ModRed.
+ * draws_short: [n][m][2] or NULL.  w_out, v_out: [m] over Z_r. */
+typedef struct { const sgo_params* P; const ntt_plan* p; const sgo_u128* key; const sgo_u128* lwes;
+                 const int64_t* draws; u128* w_acc; u128* v_acc; pthread_mutex_t lock; } pack_job;
+static void pack_row(long i, void* vp) {
+  pack_job* J = (pack_job*)vp; const sgo_params* P = J->P; int n = P->n, m = P->m; size_t M = m; u128 Q = U(P->Q);
+  u128* buf = (u128*)malloc((1 + 8 + 2 + 4) * M * sizeof(u128));
+  u128 *as = buf, *A = buf + M, *w = buf + 9 * M, *v = buf + 10 * M, *work = buf + 11 * M;
+  for (size_t k = 0; k < M; ++k) as[k] = 0;                                     /* resize(..., m)  fhe.jl:676 */
+  for (int j = 0; j < n; ++j) as[j] = U(J->lwes[(size_t)j * (n + 1) + i]);      /* new_lwes[j].a[i] */
+  for (size_t k = 0; k < 8 * M; ++k) A[k] = U(J->key[(size_t)i * 8 * M + k]);
+  shortened_product_u(J->p, as, A, U(P->B), J->draws ? J->draws + (size_t)i * 2 * M : NULL, w, v, work);   /* fhe.jl:683-684 */
+  pthread_mutex_lock(&J->lock);
+  for (size_t k = 0; k < M; ++k) { J->w_acc[k] = addmod(J->w_acc[k], w[k], Q); J->v_acc[k] = addmod(J->v_acc[k], v[k], Q); }   /* fhe.jl:686-687 */
+  pthread_mutex_unlock(&J->lock);
+  free(buf);
+}
+int sgo_pack_from_lwes(const sgo_params* P, const sgo_u128* key, const sgo_u128* new_lwes, const int64_t* draws_short,
+                       uint64_t* w_out, uint64_t* v_out) {
+  int n = P->n, m = P->m; u128 Q = U(P->Q);
+  const ntt_plan* p = get_plan(m, Q); if (!p) return -1;
+  pack_job J; J.P = P; J.p = p; J.key = key; J.lwes = new_lwes; J.draws = draws_short;
+  J.w_acc = (u128*)calloc(m, sizeof(u128)); J.v_acc = (u128*)calloc(m, sizeof(u128));
+  pthread_mutex_init(&J.lock, NULL);
+  parallel_for(n, g_setup_threads, pack_row, &J);
+  sgo_u128 r = {P->r, 0};
+  for (int k = 0; k < m; ++k) {
+    u128 bk = k < n ? U(new_lwes[(size_t)k * (n + 1) + n]) : 0;                 /* b = resize([new_lwe.b ...], m)  fhe.jl:678 */
+    u128 w1 = negmod(J.w_acc[k], Q);                                            /* fhe.jl:689 */
+    u128 v1 = submod(bk, J.v_acc[k], Q);                                        /* fhe.jl:690 */
+    w_out[k] = sgo_rescale(r, S(w1), P->Q, 1).lo;                               /* fhe.jl:692-693 */
+    v_out[k] = sgo_rescale(r, S(v1), P->Q, 1).lo;
+  }
+  free(J.w_acc); free(J.v_acc); pthread_mutex_destroy(&J.lock);
+  return 0;
+}
+
+/* fhe.jl:660-696 in full.  enc_bits [n][n+1] over Z_r; draws_boot [n][n][2][m][2] or NULL; draws_short [n][m][2] or NULL. */
+int sgo_pack_encrypted_bits(const sgo_params* P, const sgo_u128* key, const uint64_t* enc_bits, const int64_t* draws_boot,
+                            const int64_t* draws_short, uint64_t* w_out, uint64_t* v_out) {
+  int n = P->n, m = P->m; size_t L = n + 1;
+  uint64_t* triv = (uint64_t*)calloc(L, sizeof(uint64_t)); triv[n] = P->Dr;       /* fhe.jl:670-671 */
+  sgo_u128* lw = (sgo_u128*)malloc((size_t)n * L * sizeof(sgo_u128));
+  sgo_u128* scratch = (sgo_u128*)malloc(2 * L * sizeof(sgo_u128));
+  int rc = 0;
+  for (int j = 0; j < n && !rc; ++j)                                              /* fhe.jl:673, keeps [1] = AND before ModRed */
+    rc = sgo_bootstrap_internal_fast(P, key, triv, enc_bits + (size_t)j * L,
+                                     draws_boot ? draws_boot + (size_t)j * n * 4 * m : NULL, n, NULL,
+                                     lw + (size_t)j * L, scratch, scratch + L);
+  if (!rc) rc = sgo_pack_from_lwes(P, key, lw, draws_short, w_out, v_out);
+  free(triv); free(lw); free(scratch);
+  return rc;
+}
+
+/* split_ciphertext on a length-N RLWE over Z_r (Ciphertext: N = m; PackedCiphertext: N = n)  fhe.jl:287-290 */
+void sgo_split_rlwe(const sgo_params* P, int N, const uint64_t* a, const uint64_t* b, uint64_t* lwes) {
+  int n = P->n; uint64_t r = P->r;
+  for (int i = 1; i <= n; ++i) {
+    uint64_t* o = lwes + (size_t)(i - 1) * (n + 1);
+    int k = 0;
+    if (i < n) {
+      for (int j = i; j >= 1; --j) o[k++] = a[j - 1];
+      for (int j = N; j >= N - (n - i - 1); --j) o[k++] = a[j - 1] ? r - a[j - 1] : 0;
+    } else {
+      for (k = 0; k < n; ++k) o[k] = a[i - 1 - k];
+    }
+    o[n] = b[i - 1];
+  }
+}
+
+/* decrypt(key, ct::Ciphertext)  fhe.jl:471-494 (Ciphertext branch: key resized to m, first n coefficients kept) */
+void sgo_decrypt_ciphertext(const sgo_params* P, const uint8_t* sk, const uint64_t* a, const uint64_t* b, uint64_t* bits_out) {
+  int n = P->n, m = P->m; uint64_t mask = P->r - 1;
+  uint64_t* ks = (uint64_t*)calloc(m, sizeof(uint64_t));
+  for (int i = 0; i < n; ++i) {
+    if (!sk[i]) continue;
+    for (int j = 0; j < m; ++j) {
+      int k = i + j;
+      if (k < m) ks[k] = (ks[k] + a[j]) & mask; else ks[k - m] = (ks[k - m] - a[j]) & mask;
+    }
+  }
+  for (int k = 0; k < n; ++k) bits_out[k] = ((((b[k] - ks[k]) & mask) + P->Dr / 2) & mask) / P->Dr;
+  free(ks);
+}

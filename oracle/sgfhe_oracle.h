@@ -134,6 +134,20 @@ uint64_t sgo_decrypt_lwe(const sgo_params* P, const uint8_t* sk, const uint64_t*
 void sgo_decrypt_packed(const sgo_params* P, const uint8_t* sk, const uint64_t* a, const uint64_t* b,
                         uint64_t* bits_out);
 
+/* fhe.jl:632-641: A [4][2][N] coefficient form (rows 3,4 used); draws [N][2] or NULL */
+int sgo_shortened_external_product(const sgo_u128* a, const sgo_u128* A, int N, sgo_u128 B, sgo_u128 Q,
+                                   const int64_t* draws, sgo_u128* a_out, sgo_u128* b_out);
+/* fhe.jl:675-693 given new_lwes [n][n+1] wide over Z_Q; draws_short [n][m][2] or NULL; w_out, v_out [m] over Z_r */
+int sgo_pack_from_lwes(const sgo_params* P, const sgo_u128* key, const sgo_u128* new_lwes, const int64_t* draws_short,
+                       uint64_t* w_out, uint64_t* v_out);
+/* fhe.jl:660-696: enc_bits [n][n+1]; draws_boot [n][n][2][m][2] or NULL; draws_short [n][m][2] or NULL */
+int sgo_pack_encrypted_bits(const sgo_params* P, const sgo_u128* key, const uint64_t* enc_bits, const int64_t* draws_boot,
+                            const int64_t* draws_short, uint64_t* w_out, uint64_t* v_out);
+/* fhe.jl:287-290 on a length-N RLWE */
+void sgo_split_rlwe(const sgo_params* P, int N, const uint64_t* a, const uint64_t* b, uint64_t* lwes);
+/* fhe.jl:471-494, Ciphertext branch (length m) */
+void sgo_decrypt_ciphertext(const sgo_params* P, const uint8_t* sk, const uint64_t* a, const uint64_t* b, uint64_t* bits_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ def lib():
         _LIB.sgo_external_product.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, U128, U128,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.sgo_decrypt_lwe.restype = C.c_uint64
+        _LIB.sgo_shortened_external_product.argtypes = [C.c_void_p, C.c_void_p, C.c_int, U128, U128, C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
 
@@ -248,6 +249,57 @@ def decrypt_lwe(P: Params, sk, lwe) -> int:
     sk = np.ascontiguousarray(sk, np.uint8)
     lwe = np.ascontiguousarray(lwe, np.uint64)
     return int(lib().sgo_decrypt_lwe(C.byref(P.c), _p(sk), _p(lwe)))
+
+
+def shortened_external_product(a, A, B, Q, draws=None):
+    a = np.ascontiguousarray(a, np.uint64)
+    A = np.ascontiguousarray(A, np.uint64)
+    d = None if draws is None else np.ascontiguousarray(draws, np.int64)
+    oa, ob = np.zeros_like(a), np.zeros_like(a)
+    rc = lib().sgo_shortened_external_product(_p(a), _p(A), a.shape[0], u(B), u(Q), _p(d), _p(oa), _p(ob))
+    if rc:
+        raise ValueError("no NTT for this (N, Q)")
+    return oa, ob
+
+
+def pack_from_lwes(P: Params, key, new_lwes, draws_short=None):
+    key = np.ascontiguousarray(key, np.uint64)
+    new_lwes = np.ascontiguousarray(new_lwes, np.uint64)
+    d = None if draws_short is None else np.ascontiguousarray(draws_short, np.int64)
+    w, v = np.zeros(P.m, np.uint64), np.zeros(P.m, np.uint64)
+    rc = lib().sgo_pack_from_lwes(C.byref(P.c), _p(key), _p(new_lwes), _p(d), _p(w), _p(v))
+    if rc:
+        raise RuntimeError(f"sgo_pack_from_lwes -> {rc}")
+    return w, v
+
+
+def pack_encrypted_bits(P: Params, key, enc_bits, draws_boot=None, draws_short=None):
+    key = np.ascontiguousarray(key, np.uint64)
+    enc_bits = np.ascontiguousarray(enc_bits, np.uint64)
+    db = None if draws_boot is None else np.ascontiguousarray(draws_boot, np.int64)
+    ds = None if draws_short is None else np.ascontiguousarray(draws_short, np.int64)
+    w, v = np.zeros(P.m, np.uint64), np.zeros(P.m, np.uint64)
+    rc = lib().sgo_pack_encrypted_bits(C.byref(P.c), _p(key), _p(enc_bits), _p(db), _p(ds), _p(w), _p(v))
+    if rc:
+        raise RuntimeError(f"sgo_pack_encrypted_bits -> {rc}")
+    return w, v
+
+
+def split_rlwe(P: Params, a, b):
+    a = np.ascontiguousarray(a, np.uint64)
+    b = np.ascontiguousarray(b, np.uint64)
+    out = np.zeros((P.n, P.n + 1), np.uint64)
+    lib().sgo_split_rlwe(C.byref(P.c), a.shape[0], _p(a), _p(b), _p(out))
+    return out
+
+
+def decrypt_ciphertext(P: Params, sk, a, b):
+    sk = np.ascontiguousarray(sk, np.uint8)
+    a = np.ascontiguousarray(a, np.uint64)
+    b = np.ascontiguousarray(b, np.uint64)
+    out = np.zeros(P.n, np.uint64)
+    lib().sgo_decrypt_ciphertext(C.byref(P.c), _p(sk), _p(a), _p(b), _p(out))
+    return out
 
 
 def set_setup_threads(t: int):
