@@ -96,6 +96,17 @@ int sgfhe_bootstrap_trace(sgfhe_ctx* ctx, const uint64_t* lwe1, const uint64_t* 
                           int32_t n_steps, uint64_t* trace, uint64_t* out_and, uint64_t* out_or,
                           uint64_t* out_xor);
 
+/* _bootstrap_internal for a batch (src/fhe.jl:559-595): the three LWEs over Z_Q, i.e. BEFORE reduce_modulus,
+ * as pack_encrypted_bits needs them (src/fhe.jl:673).  out_*: host [batch][n+1][2] wide. */
+int sgfhe_bootstrap_internal_batch(sgfhe_ctx* ctx, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,
+                                   const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor);
+
+/* shortened_external_product(rng|nothing, polys[i], bkey.key[i], Val(B), Val(2)) for i = 0..count-1
+ * (src/fhe.jl:632-641 as called at src/fhe.jl:683-684): flatten(polys[i]) times rows 3,4 of the uploaded key row i.
+ * polys: host [count][m][2] wide; draws: NULL or [count][m][2]; out: [count][2][m][2] wide (w_i then v_i). */
+int sgfhe_shortened_products(sgfhe_ctx* ctx, int32_t count, const uint64_t* polys, const int64_t* draws,
+                             uint64_t* out);
+
 /* Negacyclic products in Z_Q[x]/(x^m+1): out[i] = a[i] * b[i], DarkIntegers `Polynomial *` as called at
  * src/fhe.jl:195,527-528.  a, b, out: host [batch][m][2] wide canonical. */
 int sgfhe_polymul(sgfhe_ctx* ctx, int32_t batch, const uint64_t* a, const uint64_t* b, uint64_t* out);

@@ -4,10 +4,10 @@ Imported as `sgfhe_jl_b200` through the shim at the repository root.
 """
 from ._lib import SO_PATH, SgfheError, build
 from .parallel import bootstrap_sharded, broadcast_key, shard_bounds
-from .api import (BootstrapKey, EncryptedBit, LWE, PackedCiphertext, Params, PrivateKey, bootstrap,
+from .api import (BootstrapKey, Ciphertext, EncryptedBit, LWE, PackedCiphertext, Params, PrivateKey, bootstrap,
                   bootstrap_batch, bootstrap_trace, decrypt, encrypt, external_product, flatten_poly,
-                  launch_count, polymul, split_ciphertext)
+                  launch_count, pack_encrypted_bits, polymul, split_ciphertext)
 
 __all__ = ["Params", "PrivateKey", "BootstrapKey", "encrypt", "decrypt", "split_ciphertext", "bootstrap",
-           "bootstrap_batch", "bootstrap_trace", "polymul", "flatten_poly", "external_product",
+           "bootstrap_batch", "bootstrap_trace", "pack_encrypted_bits", "Ciphertext", "polymul", "flatten_poly", "external_product",
            "bootstrap_sharded", "broadcast_key", "shard_bounds", "EncryptedBit", "LWE", "PackedCiphertext", "SgfheError", "build", "launch_count", "SO_PATH"]

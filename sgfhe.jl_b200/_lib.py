@@ -19,6 +19,7 @@ SYMBOLS = [
     "sgfhe_bkey_upload", "sgfhe_bootstrap_batch", "sgfhe_bootstrap_batch_device", "sgfhe_bootstrap_trace",
     "sgfhe_polymul", "sgfhe_polymul_device", "sgfhe_flatten_poly", "sgfhe_external_product",
     "sgfhe_launch_count", "sgfhe_bkey_device_buffer", "sgfhe_bkey_adopt",
+    "sgfhe_bootstrap_internal_batch", "sgfhe_shortened_products",
 ]
 
 
@@ -63,6 +64,8 @@ def lib():
         L.sgfhe_external_product.argtypes = [vp, u64p, u64p, u64p, vp, u64p, u64p]
         L.sgfhe_bkey_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.sgfhe_bkey_adopt.argtypes = [vp, i32]
+        L.sgfhe_bootstrap_internal_batch.argtypes = [vp, i32, u64p, u64p, vp, u64p, u64p, u64p]
+        L.sgfhe_shortened_products.argtypes = [vp, i32, u64p, vp, u64p]
         _LIB = L
     return _LIB
 

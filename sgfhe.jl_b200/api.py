@@ -98,6 +98,15 @@ class PackedCiphertext:
         self.b = np.asarray(b, np.uint64)
 
 
+class Ciphertext:
+    """src/fhe.jl:261-264: RLWE (a, b) over (x^m+1, r), produced by pack_encrypted_bits."""
+
+    def __init__(self, params: Params, a, b):
+        self.params = params
+        self.a = np.asarray(a, np.uint64)
+        self.b = np.asarray(b, np.uint64)
+
+
 def _negacyclic_small(a: np.ndarray, s: np.ndarray, modulus: int) -> np.ndarray:
     """a * s in Z_modulus[x]/(x^n+1) for a binary s (host; length-n ciphertext work, not the hot path)."""
     n = a.shape[0]
@@ -134,8 +143,8 @@ def _extract_r(a: np.ndarray, i: int, n: int, r: int) -> np.ndarray:
     return a[i - n:i][::-1].copy()
 
 
-def split_ciphertext(ct: PackedCiphertext) -> list[EncryptedBit]:
-    """src/fhe.jl:287-290"""
+def split_ciphertext(ct) -> list[EncryptedBit]:
+    """split_ciphertext(ct::Union{Ciphertext, PackedCiphertext}) -- src/fhe.jl:287-290"""
     P = ct.params
     return [EncryptedBit(LWE(_extract_r(ct.a, i, P.n, P.r), ct.b[i - 1])) for i in range(1, P.n + 1)]
 
@@ -149,7 +158,12 @@ def decrypt(key: PrivateKey, ct):
         if v > 1:
             raise SgfheError("InexactError: decrypted value is not a Bool (src/fhe.jl:506)")
         return bool(v)
-    b1 = (ct.b.astype(np.int64) - _negacyclic_small(ct.a, key.key, P.r).astype(np.int64)) % P.r
+    if isinstance(ct, Ciphertext):                     # key resized to m, first n coefficients kept (src/fhe.jl:474-485)
+        ext = np.zeros(P.m, np.uint8)
+        ext[: P.n] = key.key
+        b1 = ((ct.b.astype(np.int64) - _negacyclic_small(ct.a, ext, P.r).astype(np.int64)) % P.r)[: P.n]
+    else:
+        b1 = (ct.b.astype(np.int64) - _negacyclic_small(ct.a, key.key, P.r).astype(np.int64)) % P.r
     v = ((b1 + P.Dr // 2) % P.r) // P.Dr
     if (v > 1).any():
         raise SgfheError("InexactError: decrypted value is not a Bool (src/fhe.jl:493)")
@@ -267,6 +281,55 @@ def bootstrap(bkey: BootstrapKey, rng, enc_bit1: EncryptedBit, enc_bit2: Encrypt
     """bootstrap(bkey, rng|nothing, enc_bit1, enc_bit2) -> (AND, OR, XOR) -- src/fhe.jl:608-621."""
     outs = bootstrap_batch(bkey, rng, enc_bit1.lwe.flat()[None, :], enc_bit2.lwe.flat()[None, :])
     return tuple(EncryptedBit(LWE(o[0, :-1], o[0, -1])) for o in outs)
+
+
+def _wide_sum_mod(w: np.ndarray, Q: int) -> list[int]:
+    """sum over axis 0 of wide values uint64[k, ..., 2] -> flat list of Python ints mod Q (32-bit limb sums, no overflow)"""
+    limbs = np.stack([w[..., 0] & np.uint64(0xFFFFFFFF), w[..., 0] >> np.uint64(32),
+                      w[..., 1] & np.uint64(0xFFFFFFFF), w[..., 1] >> np.uint64(32)], axis=-1)
+    tot = limbs.sum(axis=0, dtype=np.uint64).reshape(-1, 4)
+    return [(int(t[0]) + (int(t[1]) << 32) + (int(t[2]) << 64) + (int(t[3]) << 96)) % Q for t in tot]
+
+
+def _rescale_round(x: int, new_max: int, old_max: int) -> int:
+    """rescale(new_max, x, old_max, round=true) -- src/utils.jl:78-92 (host copy for the m output coefficients of packing)"""
+    q, rem = divmod(x * new_max, old_max)
+    if rem >= old_max // 2 + (old_max & 1):
+        q += 1
+        if q == new_max:
+            q = 0
+    return q
+
+
+def pack_encrypted_bits(bkey: BootstrapKey, rng, enc_bits) -> Ciphertext:
+    """pack_encrypted_bits(bkey, rng|nothing, enc_bits) -- src/fhe.jl:660-696.
+
+    The n internal bootstraps (src/fhe.jl:673) and the n shortened external products (src/fhe.jl:683-684) run on the
+    GPU; the transposition, the two sums over i and the final ModRed of 2m coefficients are host work."""
+    P = bkey.params
+    if len(enc_bits) != P.n:
+        raise SgfheError("expected n encrypted bits (src/fhe.jl:667)")
+    bkey.upload()
+    L = _lib.lib()
+    n, m = P.n, P.m
+    triv = np.zeros((n, n + 1), np.uint64)
+    triv[:, n] = P.Dr                                                     # trivial LWE encrypting 1, src/fhe.jl:670-671
+    bits = np.ascontiguousarray(np.stack([e.lwe.flat() for e in enc_bits]), np.uint64)
+    draws = None if rng is None else _draws(P, rng, (n, n, 2, m, 2))
+    outs = [np.zeros((n, n + 1, 2), np.uint64) for _ in range(3)]
+    check(L.sgfhe_bootstrap_internal_batch(P.ctx, n, _ptr(triv), _ptr(bits), _ptr(draws), *[_ptr(o) for o in outs]))
+    new_lwes = outs[0]                                                    # [1] = AND output, before ModRed (src/fhe.jl:673)
+    polys = np.zeros((n, m, 2), np.uint64)
+    polys[:, :n, :] = np.transpose(new_lwes[:, :n, :], (1, 0, 2))         # as[i][j] = new_lwes[j].a[i], resized to m (:675-677)
+    ds = None if rng is None else _draws(P, rng, (n, m, 2))
+    wv = np.zeros((n, 2, m, 2), np.uint64)
+    check(L.sgfhe_shortened_products(P.ctx, n, _ptr(polys), _ptr(ds), _ptr(wv)))
+    tot = _wide_sum_mod(wv, P.Q)                                          # w_tilde, v_tilde (src/fhe.jl:686-687)
+    w_t, v_t = tot[:m], tot[m:]
+    b = [_wide_to_int(new_lwes[j, n]) if j < n else 0 for j in range(m)]  # src/fhe.jl:678
+    w = [_rescale_round((-x) % P.Q, P.r, P.Q) for x in w_t]               # src/fhe.jl:689, 692
+    v = [_rescale_round((bj - x) % P.Q, P.r, P.Q) for bj, x in zip(b, v_t)]   # src/fhe.jl:690, 693
+    return Ciphertext(P, np.array(w, np.uint64), np.array(v, np.uint64))
 
 
 # ---- inner seams (test/internals.test.jl level) ---------------------------------------------------------

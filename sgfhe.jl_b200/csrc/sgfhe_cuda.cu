@@ -22,7 +22,7 @@ using namespace sgfhe;
 // Kernels
 // =========================================================================================================
 
-enum : int { F_INIT = 1, F_FINAL = 2, F_RAW = 4, F_EXT = 8, F_DECOMP = 16 };
+enum : int { F_INIT = 1, F_FINAL = 2, F_RAW = 4, F_EXT = 8, F_DECOMP = 16, F_PACK = 32 };
 
 struct GateArgs {
   const uint64_t* lwe1; const uint64_t* lwe2;   // [batch][n+1] over Z_r
@@ -35,6 +35,8 @@ struct GateArgs {
   uint8_t* zres; size_t zres_stride;            // per CTA: inverse-transform residues
   int batch, step_begin, step_end, draw_steps, flags;
   unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
+  const uint64_t* pack_in;                      // F_PACK: [batch][m][2] wide polynomials, job g multiplies poly g with key row g
+  const int64_t* pack_draws;                    // F_PACK: NULL or [batch][m][2]
   int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
 
@@ -323,25 +325,36 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
+    const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
     const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
     if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
-    __syncthreads();
-    if ((A.flags & F_DECOMP) && A.step_begin < A.step_end) {
-      decompose_poly<LOGM>(C, S, 0, dr);
-      decompose_poly<LOGM>(C, S, 1, dr);
+    if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
+      u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
+      for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        const uint64_t* src = A.pack_in + ((size_t)g * m + e) * 2;
+        u96 v; v.x0 = (uint32_t)src[0]; v.x1 = (uint32_t)(src[0] >> 32); v.x2 = (uint32_t)src[1];
+        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, v);
+      }
     }
     __syncthreads();
-    for (int k = A.step_begin; k < A.step_end; ++k) {
+    const int k_begin = pack ? g : A.step_begin, k_end = pack ? g + 1 : A.step_end;
+    if ((A.flags & F_DECOMP) && k_begin < k_end) {
+      decompose_poly<LOGM>(C, S, 0, pack ? nullptr : dr);
+      decompose_poly<LOGM>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
+    }
+    __syncthreads();
+    for (int k = k_begin; k < k_end; ++k) {
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
-      const bool more = k + 1 < A.step_end;
+      const bool more = k + 1 < k_end;
       gate_step<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i,
-                      (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
+                      (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
                       tab, bar, parity, blockIdx.x == 0 ? A.timing : nullptr);
     }
     if (A.trace) {
+      uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
         const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
-        A.trace[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); A.trace[2 * e + 1] = v.x2;
+        tr[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); tr[2 * e + 1] = v.x2;
       }
     }
     if (A.flags & F_FINAL) {
@@ -598,25 +611,36 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
+    const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
     const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
     if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
-    __syncthreads();
-    if ((A.flags & F_DECOMP) && A.step_begin < A.step_end) {
-      decompose_poly<LOGM>(C, S, 0, dr);
-      decompose_poly<LOGM>(C, S, 1, dr);
+    if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
+      u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
+      for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        const uint64_t* src = A.pack_in + ((size_t)g * m + e) * 2;
+        u96 v; v.x0 = (uint32_t)src[0]; v.x1 = (uint32_t)(src[0] >> 32); v.x2 = (uint32_t)src[1];
+        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, v);
+      }
     }
     __syncthreads();
-    for (int k = A.step_begin; k < A.step_end; ++k) {
+    const int k_begin = pack ? g : A.step_begin, k_end = pack ? g + 1 : A.step_end;
+    if ((A.flags & F_DECOMP) && k_begin < k_end) {
+      decompose_poly<LOGM>(C, S, 0, pack ? nullptr : dr);
+      decompose_poly<LOGM>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
+    }
+    __syncthreads();
+    for (int k = k_begin; k < k_end; ++k) {
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
-      const bool more = k + 1 < A.step_end;
+      const bool more = k + 1 < k_end;
       gate_step_v4<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f,
-                         (dr && more) ? dr + (size_t)(k + 1 - A.step_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
+                         (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
                          tab, bar, toptw, parity, pc, blockIdx.x == 0 ? A.timing : nullptr);
     }
     if (A.trace) {
+      uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
         const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
-        A.trace[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); A.trace[2 * e + 1] = v.x2;
+        tr[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); tr[2 * e + 1] = v.x2;
       }
     }
     if (A.flags & F_FINAL) {
@@ -1146,6 +1170,69 @@ extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t
   cudaFree(d_io); cudaFree(d_draws);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_batch: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+
+extern "C" int sgfhe_bootstrap_internal_batch(sgfhe_ctx* c, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,
+                                              const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor) {
+  if (!c || !lwe1 || !lwe2 || !out_and || !out_or || !out_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t lwe_w = (size_t)batch * (c->hp.n + 1);
+  const size_t draw_bytes = draws ? (size_t)batch * c->hp.n * 4 * c->hp.m * sizeof(int64_t) : 0;
+  uint64_t* d_io = nullptr; int64_t* d_draws = nullptr;
+  if (cudaMalloc(&d_io, (2 + 6) * lwe_w * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of LWE buffers failed");
+  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) { cudaFree(d_io); return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed"); }
+  int rc = SGFHE_OK;
+  cudaError_t e = cudaMemcpy(d_io, lwe1, lwe_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_io + lwe_w, lwe2, lwe_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    GateArgs A; memset(&A, 0, sizeof A);
+    A.lwe1 = d_io; A.lwe2 = d_io + lwe_w; A.draws = d_draws;
+    A.out_and = d_io + 2 * lwe_w; A.out_or = d_io + 4 * lwe_w; A.out_xor = d_io + 6 * lwe_w;
+    A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL | F_RAW;
+    rc = launch_gates(c, A, nullptr);
+    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_and, d_io + 2 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_or, d_io + 4 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_xor, d_io + 6 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
+  cudaFree(d_io); cudaFree(d_draws);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_internal_batch: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_shortened_products(sgfhe_ctx* c, int32_t count, const uint64_t* polys, const int64_t* draws,
+                                        uint64_t* out) {
+  if (!c || !polys || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count < 0 || count > c->key_rows) return fail(count < 0 ? SGFHE_ERR_ARG : SGFHE_ERR_STATE, "count exceeds the uploaded key rows");
+  if (count == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t m = c->hp.m, in_w = (size_t)count * m * 2, out_w = (size_t)count * 4 * m;
+  uint64_t* d = nullptr; int64_t* d_draws = nullptr;
+  if (cudaMalloc(&d, (in_w + out_w + 8) * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  if (draws && cudaMalloc(&d_draws, in_w * 8) != cudaSuccess) { cudaFree(d); return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed"); }
+  int rc = SGFHE_OK;
+  cudaError_t e = cudaMemcpy(d, polys, in_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, in_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    GateArgs A; memset(&A, 0, sizeof A);
+    uint64_t* dummy = d + in_w + out_w;
+    A.lwe1 = dummy; A.lwe2 = dummy; A.out_and = A.out_or = A.out_xor = dummy;
+    A.batch = count; A.flags = F_EXT | F_DECOMP | F_PACK;
+    A.pack_in = d; A.pack_draws = d_draws; A.trace = d + in_w;
+    rc = launch_gates(c, A, nullptr);
+    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out, d + in_w, out_w * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d); cudaFree(d_draws);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("shortened_products: ") + cudaGetErrorString(e));
   return SGFHE_OK;
 }
 

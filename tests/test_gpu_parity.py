@@ -188,3 +188,50 @@ def test_bootstrap_trace_truncated_large(so, sg, n):
             assert np.array_equal(gtr[k], rtr[k]), f"accumulator differs after step {k}"
         assert np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
     P.close()
+
+
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_pack_encrypted_bits_p64(env64, so, sg, use_rng):
+    """port of test/api.test.jl:86-108 (packing): pack -> split -> decrypt and pack -> decrypt both give the message;
+    and the packed RLWE equals the oracle's pack_encrypted_bits (src/fhe.jl:660-696) bit for bit."""
+    P, OP, sk, key, bits, lwes, bkey = env64
+
+    class _Rng:                                       # hands the library pre-drawn values in the reference's order
+        def __init__(self, arrays): self.arrays = list(arrays)
+        def integers(self, lo, hi, size, dtype): return self.arrays.pop(0)
+
+    xmax = OP.B // 2 * 3
+    gen = np.random.default_rng(41)
+    db = gen.integers(-xmax, xmax + 1, size=(OP.n, OP.n, 2, OP.m, 2), dtype=np.int64) if use_rng else None
+    ds = gen.integers(-xmax, xmax + 1, size=(OP.n, OP.m, 2), dtype=np.int64) if use_rng else None
+    ebits = [sg.EncryptedBit(sg.LWE(l[:-1], l[-1])) for l in lwes]
+    ct = sg.pack_encrypted_bits(bkey, _Rng([db, ds]) if use_rng else None, ebits)
+    rw, rv = so.pack_encrypted_bits(OP, key, lwes, db, ds)
+    assert np.array_equal(ct.a, rw) and np.array_equal(ct.b, rv)
+    key_obj = type("K", (), {"params": P, "key": sk})()
+    assert np.array_equal(sg.decrypt(key_obj, ct), bits.astype(bool))
+    assert [sg.decrypt(key_obj, e) for e in sg.split_ciphertext(ct)] == [bool(b) for b in bits]
+
+
+def test_shortened_products_match_oracle_p1024(so, sg):
+    """shortened_external_product at paper size (src/fhe.jl:632-641) against the oracle, both flatten modes"""
+    import ctypes as C
+    from sgfhe_jl_b200 import _lib
+    P, OP = sg.Params(1024), so.Params(1024)
+    rows = 2
+    sk = so.make_secret(OP, 1)
+    key = so.make_bkey(OP, sk, 1, rows=rows)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    bkey.upload()
+    rng = np.random.default_rng(51)
+    polys = so.rand_below(rng, OP.Q, (rows, OP.m))
+    xmax = OP.B // 2 * 3
+    for draws in (None, rng.integers(-xmax, xmax + 1, size=(rows, OP.m, 2), dtype=np.int64)):
+        out = np.zeros((rows, 2, OP.m, 2), np.uint64)
+        _lib.check(_lib.lib().sgfhe_shortened_products(P.ctx, rows, polys.ctypes.data_as(C.c_void_p),
+                                                       None if draws is None else draws.ctypes.data_as(C.c_void_p),
+                                                       out.ctypes.data_as(C.c_void_p)))
+        for i in range(rows):
+            w, v = so.shortened_external_product(polys[i], key[i], OP.B, OP.Q, None if draws is None else draws[i])
+            assert np.array_equal(out[i, 0], w) and np.array_equal(out[i, 1], v)
+    P.close()

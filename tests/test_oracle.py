@@ -244,3 +244,36 @@ def test_oracle_reproduces_golden(so, name):
                                                 trace=True, fast=(n > 64))
             assert np.array_equal(a, g[tag + "_and_Q"]) and np.array_equal(o, g[tag + "_or_Q"]) and np.array_equal(x, g[tag + "_xor_Q"])
             assert [sha(tr[k]) for k in range(steps)] == [str(s) for s in g[tag + "_trace_sha256"]]
+
+
+@pytest.mark.parametrize("use_rng", [False, True])
+def test_pack_encrypted_bits(so, gate64, use_rng):
+    """port of test/api.test.jl:86-108: pack -> split -> decrypt and pack -> decrypt give the message"""
+    P, sk, key, bits, lwes = gate64
+    xmax = P.B // 2 * 3
+    gen = np.random.default_rng(17)
+    db = gen.integers(-xmax, xmax + 1, size=(P.n, P.n, 2, P.m, 2), dtype=np.int64) if use_rng else None
+    ds = gen.integers(-xmax, xmax + 1, size=(P.n, P.m, 2), dtype=np.int64) if use_rng else None
+    w, v = so.pack_encrypted_bits(P, key, lwes, db, ds)
+    assert np.array_equal(so.decrypt_ciphertext(P, sk, w, v), bits)
+    l2 = so.split_rlwe(P, w, v)
+    assert [so.decrypt_lwe(P, sk, l2[i]) for i in range(P.n)] == bits.tolist()
+
+
+def test_pack_oracle_equals_model(so, gate64):
+    """shortened_external_product + the assembly of src/fhe.jl:675-693 against the big-integer model"""
+    P, sk, key, bits, lwes = gate64
+    M = md.params(64)
+    triv = np.zeros(P.n + 1, np.uint64); triv[P.n] = P.Dr
+    nl = np.stack([so.bootstrap_internal(P, key, triv, lwes[j], fast=True)[0] for j in range(P.n)])
+    w, v = so.pack_from_lwes(P, key, nl)
+    mw, mv = md.pack_from_lwes(M, so.unpack(key), so.unpack(nl))
+    assert mw == w.tolist() and mv == v.tolist()
+    rng = np.random.default_rng(9)
+    a = so.rand_below(rng, P.Q, (P.m,))
+    xmax = P.B // 2 * 3
+    d = rng.integers(-xmax, xmax + 1, size=(P.m, 2), dtype=np.int64)
+    for dr in (None, d):
+        oa, ob = so.shortened_external_product(a, key[5], P.B, P.Q, dr)
+        ma, mb = md.shortened_external_product(so.unpack(a), so.unpack(key[5]), P.B, P.Q, None if dr is None else dr.tolist())
+        assert so.unpack(oa) == ma and so.unpack(ob) == mb
