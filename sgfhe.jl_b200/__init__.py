@@ -3,6 +3,7 @@
 Imported as `sgfhe_jl_b200` through the shim at the repository root.
 """
 from ._lib import SO_PATH, SgfheError, build
+from .chain import bootstrap_chain
 from .parallel import bootstrap_sharded, broadcast_key, shard_bounds
 from .api import (BootstrapKey, Ciphertext, EncryptedBit, LWE, PackedCiphertext, Params, PrivateKey, bootstrap,
                   bootstrap_batch, bootstrap_trace, decrypt, encrypt, external_product, flatten_poly,
@@ -10,4 +11,4 @@ from .api import (BootstrapKey, Ciphertext, EncryptedBit, LWE, PackedCiphertext,
 
 __all__ = ["Params", "PrivateKey", "BootstrapKey", "encrypt", "decrypt", "split_ciphertext", "bootstrap",
            "bootstrap_batch", "bootstrap_trace", "pack_encrypted_bits", "Ciphertext", "polymul", "flatten_poly", "external_product",
-           "bootstrap_sharded", "broadcast_key", "shard_bounds", "EncryptedBit", "LWE", "PackedCiphertext", "SgfheError", "build", "launch_count", "SO_PATH"]
+           "bootstrap_chain", "bootstrap_sharded", "broadcast_key", "shard_bounds", "EncryptedBit", "LWE", "PackedCiphertext", "SgfheError", "build", "launch_count", "SO_PATH"]

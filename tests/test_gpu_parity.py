@@ -235,3 +235,23 @@ def test_shortened_products_match_oracle_p1024(so, sg):
             w, v = so.shortened_external_product(polys[i], key[i], OP.B, OP.Q, None if draws is None else draws[i])
             assert np.array_equal(out[i, 0], w) and np.array_equal(out[i, 1], v)
     P.close()
+
+
+def test_chained_layers_match_oracle_p64(env64, so, sg):
+    """examples/depth.jl:63-78 pattern: 4 layers of 6 gates with (AND, XOR) fed back in, ciphertexts resident on the
+    device; every layer equals the oracle's bootstrap() and decrypts to the plaintext circuit."""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    W, layers = 6, 4
+    l1, l2 = lwes[:W].copy(), lwes[W:2 * W].copy()
+    y1, y2 = bits[:W].astype(int), bits[W:2 * W].astype(int)
+    got = sg.bootstrap_chain(bkey, l1, l2, layers, keep_layers=True)
+    for layer in range(layers):
+        ref = so.bootstrap_batch(OP, key, l1, l2, literal=False, threads=4)
+        for g, r in zip(got[layer], ref):
+            assert np.array_equal(g, r), f"layer {layer}"
+        want = (y1 & y2, y1 | y2, y1 ^ y2)
+        for arr, w in zip(ref, want):
+            assert [so.decrypt_lwe(OP, sk, arr[i]) for i in range(W)] == w.tolist()
+        l1, l2, y1, y2 = ref[0], ref[2], want[0], want[2]
+    last = sg.bootstrap_chain(bkey, lwes[:W], lwes[W:2 * W], layers)
+    assert all(np.array_equal(a, b) for a, b in zip(last, got[-1]))
