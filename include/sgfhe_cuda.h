@@ -123,6 +123,19 @@ int sgfhe_flatten_poly(sgfhe_ctx* ctx, const uint64_t* a, const int64_t* draws, 
 int sgfhe_external_product(sgfhe_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* A,
                            const int64_t* draws, uint64_t* a_out, uint64_t* b_out);
 
+/* Scheme 2 (src/fhe2.jl, "experimental, not finished" upstream: it defines Params, keys, encrypt/decrypt and NO
+ * bootstrap).  What exists upstream and is mirrored here: Params(k) (src/fhe2.jl:36-70) and the arithmetic of
+ * its ring element type RNS2Number{UInt64, B, Bp} (src/rns.jl:51-60), batched. */
+typedef struct { int32_t n, k, t, pad; uint64_t r, m, q, tau, B, Bp, Dr, Dq; } sgfhe_scheme2_params;
+int sgfhe_scheme2_params_derive(int32_t k, sgfhe_scheme2_params* out);
+/* out = a op b limb-wise, op 0 = * (rns.jl:51-52), 1 = + (rns.jl:55-56), 2 = - (rns.jl:59-60); host buffers of `count` */
+int sgfhe_rns2_op(int32_t device, int32_t op, uint64_t count, const uint64_t* a1, const uint64_t* a2,
+                  const uint64_t* b1, const uint64_t* b2, uint64_t M1, uint64_t M2, uint64_t* o1, uint64_t* o2);
+/* same with device buffers, asynchronous on `stream` */
+int sgfhe_rns2_op_device(int32_t device, int32_t op, uint64_t count, const uint64_t* d_a1, const uint64_t* d_a2,
+                         const uint64_t* d_b1, const uint64_t* d_b2, uint64_t M1, uint64_t M2, uint64_t* d_o1,
+                         uint64_t* d_o2, void* stream);
+
 /* Kernel launches issued by this library in the calling process since load (for bench accounting). */
 uint64_t sgfhe_launch_count(void);
 

@@ -799,3 +799,36 @@ void sgo_decrypt_ciphertext(const sgo_params* P, const uint8_t* sk, const uint64
   for (int k = 0; k < n; ++k) bits_out[k] = ((((b[k] - ks[k]) & mask) + P->Dr / 2) & mask) / P->Dr;
   free(ks);
 }
+
+/* ---- Scheme 2 (src/fhe2.jl, src/rns.jl): parameters and the two-residue element type only; upstream has no
+ * flatten / external product / bootstrap for this type (src/fhe2.jl:1-7). ------------------------------------ */
+static uint64_t isqrt_u64(uint64_t x) { uint64_t r = 0; while ((r + 1) * (r + 1) <= x) ++r; return r; }
+
+/* src/fhe2.jl:36-70.  returns 0 / -1 (k out of 1..5, src/fhe2.jl:39) */
+int sgo_scheme2_params(int k, sgo_scheme2_params_t* out) {
+  if (k < 1 || k > 5) return -1;
+  uint64_t n = 1024;                                               /* fhe2.jl:41 */
+  uint64_t r = ((uint64_t)1 << (k + 6)) * isqrt_u64(n);            /* fhe2.jl:43 */
+  uint64_t m = r / 2, l = 2;                                       /* fhe2.jl:44-45 */
+  int t = 0; while (((uint64_t)1 << t) < r) ++t; t -= 1;           /* fhe2.jl:46 */
+  sgo_u128 q, Bp, B;
+  if (sgo_find_modulus(S(2 * n), S((u128)128 * r * n), S(0), &q)) return -2;          /* fhe2.jl:48 */
+  uint64_t tau = 2 * isqrt_u64(n);                                 /* fhe2.jl:51 */
+  u128 bmin = (u128)15 * ((u128)1 << (2 * k + 2)) * r * tau * isqrt_u64(2 * l * m);   /* fhe2.jl:57 */
+  if (sgo_find_modulus(S(r), S(bmin), S(0), &Bp)) return -2;
+  if (sgo_find_modulus(S(r), S(U(Bp) + 1), S(0), &B)) return -2;  /* fhe2.jl:58 */
+  out->n = (int32_t)n; out->k = k; out->r = r; out->m = m; out->t = t; out->q = q.lo; out->tau = tau;
+  out->B = B.lo; out->Bp = Bp.lo;
+  out->Dr = r >> (k + 2); out->Dq = q.lo >> (k + 2);               /* fhe2.jl:62-63 */
+  return 0;
+}
+
+/* src/rns.jl:51-60: op 0 = *, 1 = +, 2 = -, limb-wise on (v1 mod M1, v2 mod M2) */
+void sgo_rns2_op(int op, size_t count, const uint64_t* a1, const uint64_t* a2, const uint64_t* b1, const uint64_t* b2,
+                 uint64_t M1, uint64_t M2, uint64_t* o1, uint64_t* o2) {
+  for (size_t i = 0; i < count; ++i) {
+    if (op == 0) { o1[i] = (uint64_t)((u128)a1[i] * b1[i] % M1); o2[i] = (uint64_t)((u128)a2[i] * b2[i] % M2); }          /* rns.jl:51-52 */
+    else if (op == 1) { o1[i] = (uint64_t)(((u128)a1[i] + b1[i]) % M1); o2[i] = (uint64_t)(((u128)a2[i] + b2[i]) % M2); } /* rns.jl:55-56 */
+    else { o1[i] = (uint64_t)(((u128)a1[i] + M1 - b1[i]) % M1); o2[i] = (uint64_t)(((u128)a2[i] + M2 - b2[i]) % M2); }   /* rns.jl:59-60 */
+  }
+}

@@ -28,6 +28,7 @@
 #ifndef SGFHE_ORACLE_H
 #define SGFHE_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -147,6 +148,13 @@ int sgo_pack_encrypted_bits(const sgo_params* P, const sgo_u128* key, const uint
 void sgo_split_rlwe(const sgo_params* P, int N, const uint64_t* a, const uint64_t* b, uint64_t* lwes);
 /* fhe.jl:471-494, Ciphertext branch (length m) */
 void sgo_decrypt_ciphertext(const sgo_params* P, const uint8_t* sk, const uint64_t* a, const uint64_t* b, uint64_t* bits_out);
+
+/* Scheme 2 (src/fhe2.jl:17-70) */
+typedef struct { int32_t n, k, t, pad; uint64_t r, m, q, tau, B, Bp, Dr, Dq; } sgo_scheme2_params_t;
+int sgo_scheme2_params(int k, sgo_scheme2_params_t* out);
+/* RNS2Number arithmetic (src/rns.jl:51-60): op 0 = *, 1 = +, 2 = - */
+void sgo_rns2_op(int op, size_t count, const uint64_t* a1, const uint64_t* a2, const uint64_t* b1, const uint64_t* b2,
+                 uint64_t M1, uint64_t M2, uint64_t* o1, uint64_t* o2);
 
 #ifdef __cplusplus
 }

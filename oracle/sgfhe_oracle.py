@@ -302,6 +302,27 @@ def decrypt_ciphertext(P: Params, sk, a, b):
     return out
 
 
+class Scheme2ParamsC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("k", C.c_int32), ("t", C.c_int32), ("pad", C.c_int32)] + \
+               [(f, C.c_uint64) for f in ("r", "m", "q", "tau", "B", "Bp", "Dr", "Dq")]
+
+
+def scheme2_params(k: int) -> Scheme2ParamsC:
+    out = Scheme2ParamsC()
+    rc = lib().sgo_scheme2_params(k, C.byref(out))
+    if rc:
+        raise ValueError(f"sgo_scheme2_params({k}) -> {rc}")
+    return out
+
+
+def rns2_op(op: int, a1, a2, b1, b2, M1: int, M2: int):
+    arrs = [np.ascontiguousarray(x, np.uint64) for x in (a1, a2, b1, b2)]
+    o1, o2 = np.zeros_like(arrs[0]), np.zeros_like(arrs[0])
+    lib().sgo_rns2_op.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib().sgo_rns2_op(op, arrs[0].size, *[_p(x) for x in arrs], M1, M2, _p(o1), _p(o2))
+    return o1, o2
+
+
 def set_setup_threads(t: int):
     lib().sgo_set_setup_threads(int(t))
 

@@ -20,6 +20,7 @@ SYMBOLS = [
     "sgfhe_polymul", "sgfhe_polymul_device", "sgfhe_flatten_poly", "sgfhe_external_product",
     "sgfhe_launch_count", "sgfhe_bkey_device_buffer", "sgfhe_bkey_adopt",
     "sgfhe_bootstrap_internal_batch", "sgfhe_shortened_products",
+    "sgfhe_scheme2_params_derive", "sgfhe_rns2_op", "sgfhe_rns2_op_device",
 ]
 
 
@@ -66,8 +67,16 @@ def lib():
         L.sgfhe_bkey_adopt.argtypes = [vp, i32]
         L.sgfhe_bootstrap_internal_batch.argtypes = [vp, i32, u64p, u64p, vp, u64p, u64p, u64p]
         L.sgfhe_shortened_products.argtypes = [vp, i32, u64p, vp, u64p]
+        L.sgfhe_scheme2_params_derive.argtypes = [i32, C.POINTER(Scheme2ParamsC)]
+        L.sgfhe_rns2_op.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p]
+        L.sgfhe_rns2_op_device.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, vp]
         _LIB = L
     return _LIB
+
+
+class Scheme2ParamsC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("k", C.c_int32), ("t", C.c_int32), ("pad", C.c_int32)] + \
+               [(f, C.c_uint64) for f in ("r", "m", "q", "tau", "B", "Bp", "Dr", "Dq")]
 
 
 class SgfheError(RuntimeError):

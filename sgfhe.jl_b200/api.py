@@ -383,3 +383,24 @@ def bootstrap_trace(bkey: BootstrapKey, draws, lwe1, lwe2, n_steps: int | None =
 
 def launch_count() -> int:
     return int(_lib.lib().sgfhe_launch_count())
+
+
+# ---- Scheme 2 (src/fhe2.jl, src/rns.jl): parameters and element arithmetic only (upstream has no bootstrap) ----------
+class Scheme2Params:
+    """Scheme2.Params(k) -- src/fhe2.jl:17-70"""
+
+    def __init__(self, k: int):
+        pc = _lib.Scheme2ParamsC()
+        check(_lib.lib().sgfhe_scheme2_params_derive(int(k), C.byref(pc)))
+        for f in ("n", "k", "t", "r", "m", "q", "tau", "B", "Bp", "Dr", "Dq"):
+            setattr(self, f, getattr(pc, f))
+        self.Q = self.B * self.Bp
+
+
+def rns2_op(op: str, a, b, M1: int, M2: int, device: int = 0):
+    """RNS2Number{UInt64, M1, M2} arithmetic, batched (src/rns.jl:51-60).  a, b: pairs (v1, v2) of uint64 arrays."""
+    code = {"*": 0, "+": 1, "-": 2}[op]
+    arrs = [np.ascontiguousarray(x, np.uint64) for x in (a[0], a[1], b[0], b[1])]
+    o1, o2 = np.zeros_like(arrs[0]), np.zeros_like(arrs[0])
+    check(_lib.lib().sgfhe_rns2_op(device, code, arrs[0].size, *[_ptr(x) for x in arrs], M1, M2, _ptr(o1), _ptr(o2)))
+    return o1, o2

@@ -777,6 +777,29 @@ __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_
   }
 }
 
+
+// ---- Scheme 2 element type (src/rns.jl:8-60): limb-wise arithmetic on (v mod M1, v mod M2), M < 2^48 ------------
+__device__ __forceinline__ uint64_t mulmod48(uint64_t a, uint64_t b, uint64_t M, double Minv) {
+  const uint64_t q = (uint64_t)((double)a * (double)b * Minv);      // within 1 of floor(a b / M)
+  int64_t r = (int64_t)(a * b - q * M);                              // exact modulo 2^64, true value in (-M, 2M)
+  if (r < 0) r += (int64_t)M;
+  if (r >= (int64_t)M) r -= (int64_t)M;
+  return (uint64_t)r;
+}
+__global__ void rns2_kernel(int op, size_t count, const uint64_t* __restrict__ a1, const uint64_t* __restrict__ a2,
+                            const uint64_t* __restrict__ b1, const uint64_t* __restrict__ b2, uint64_t M1, uint64_t M2,
+                            uint64_t* __restrict__ o1, uint64_t* __restrict__ o2) {
+  const double i1 = 1.0 / (double)M1, i2 = 1.0 / (double)M2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t x1 = a1[i], x2 = a2[i], y1 = b1[i], y2 = b2[i];
+    uint64_t r1, r2;
+    if (op == 0) { r1 = mulmod48(x1, y1, M1, i1); r2 = mulmod48(x2, y2, M2, i2); }                          // rns.jl:51-52
+    else if (op == 1) { r1 = x1 + y1; r1 = r1 >= M1 ? r1 - M1 : r1; r2 = x2 + y2; r2 = r2 >= M2 ? r2 - M2 : r2; }   // rns.jl:55-56
+    else { r1 = x1 >= y1 ? x1 - y1 : x1 + M1 - y1; r2 = x2 >= y2 ? x2 - y2 : x2 + M2 - y2; }              // rns.jl:59-60
+    o1[i] = r1; o2[i] = r2;
+  }
+}
+
 // wide [2][m][2] -> accumulator scratch (SoA limbs) and back
 __global__ void acc_load_kernel(int m, const uint64_t* __restrict__ ab, uint32_t* acc) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1276,6 +1299,66 @@ extern "C" int sgfhe_bootstrap_trace(sgfhe_ctx* c, const uint64_t* lwe1, const u
   cudaFree(d_buf); cudaFree(d_draws);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_trace: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+
+static uint64_t h_isqrt(uint64_t x) { uint64_t r = 0; while ((r + 1) * (r + 1) <= x) ++r; return r; }
+
+extern "C" int sgfhe_scheme2_params_derive(int32_t k, sgfhe_scheme2_params* out) {
+  if (!out) return fail(SGFHE_ERR_ARG, "out is NULL");
+  if (k < 1 || k > 5) return fail(SGFHE_ERR_ARG, "k must be in 1..5 (src/fhe2.jl:39)");
+  const uint64_t n = 1024, r = ((uint64_t)1 << (k + 6)) * h_isqrt(n), m = r / 2, l = 2, tau = 2 * h_isqrt(n);
+  int t = 0; while (((uint64_t)1 << t) < r) ++t;
+  const u128 q = h_find_modulus(2 * n, (u128)128 * r * n, 0);
+  const u128 Bp = h_find_modulus(r, (u128)15 * ((u128)1 << (2 * k + 2)) * r * tau * h_isqrt(2 * l * m), 0);
+  const u128 B = h_find_modulus(r, Bp + 1, 0);
+  out->n = (int32_t)n; out->k = k; out->t = t - 1; out->pad = 0; out->r = r; out->m = m; out->q = (uint64_t)q; out->tau = tau;
+  out->B = (uint64_t)B; out->Bp = (uint64_t)Bp; out->Dr = r >> (k + 2); out->Dq = (uint64_t)q >> (k + 2);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_rns2_op_device(int32_t device, int32_t op, uint64_t count, const uint64_t* d_a1, const uint64_t* d_a2,
+                                    const uint64_t* d_b1, const uint64_t* d_b2, uint64_t M1, uint64_t M2, uint64_t* d_o1,
+                                    uint64_t* d_o2, void* stream) {
+  if (!d_a1 || !d_a2 || !d_b1 || !d_b2 || !d_o1 || !d_o2) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (op < 0 || op > 2) return fail(SGFHE_ERR_ARG, "op must be 0 (*), 1 (+) or 2 (-)");
+  if (M1 < 2 || M2 < 2 || M1 >= ((uint64_t)1 << 48) || M2 >= ((uint64_t)1 << 48)) return fail(SGFHE_ERR_ARG, "moduli must be below 2^48");
+  if (count == 0) return SGFHE_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SGFHE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256;
+  size_t blocks = (count + threads - 1) / threads;
+  const size_t cap = (size_t)prop.multiProcessorCount * 8;
+  if (blocks > cap) blocks = cap;
+  rns2_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(op, count, d_a1, d_a2, d_b1, d_b2, M1, M2, d_o1, d_o2);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_rns2_op(int32_t device, int32_t op, uint64_t count, const uint64_t* a1, const uint64_t* a2,
+                             const uint64_t* b1, const uint64_t* b2, uint64_t M1, uint64_t M2, uint64_t* o1, uint64_t* o2) {
+  if (!a1 || !a2 || !b1 || !b2 || !o1 || !o2) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count == 0) return SGFHE_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SGFHE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  CK(cudaSetDevice(device));
+  uint64_t* d = nullptr;
+  const size_t w = count;
+  if (cudaMalloc(&d, 6 * w * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  const uint64_t* src[4] = {a1, a2, b1, b2};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaMemcpy(d + i * w, src[i], w * 8, cudaMemcpyHostToDevice);
+  int rc = SGFHE_OK;
+  if (e == cudaSuccess) { rc = sgfhe_rns2_op_device(device, op, count, d, d + w, d + 2 * w, d + 3 * w, M1, M2, d + 4 * w, d + 5 * w, nullptr); if (!rc) e = cudaDeviceSynchronize(); }
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(o1, d + 4 * w, w * 8, cudaMemcpyDeviceToHost);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(o2, d + 5 * w, w * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("rns2_op: ") + cudaGetErrorString(e));
   return SGFHE_OK;
 }
 

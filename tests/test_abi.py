@@ -103,3 +103,14 @@ def test_wide_add_small(sg):
     for k in range(len(e)):
         want = (vals[k // len(es)] + es[k % len(es)]) % Q
         assert int(got[k, 0]) | (int(got[k, 1]) << 64) == want
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_scheme2_params_match_oracle(sg, so, k):
+    """Scheme2.Params(k), src/fhe2.jl:36-70"""
+    P, OP = sg.Scheme2Params(k), so.scheme2_params(k)
+    for f in ("n", "k", "t", "r", "m", "q", "tau", "B", "Bp", "Dr", "Dq"):
+        assert getattr(P, f) == getattr(OP, f), f
+    assert (P.B - 1) % P.r == 0 and (P.Bp - 1) % P.r == 0 and P.Bp < P.B
+    with pytest.raises(sg.SgfheError):
+        sg.Scheme2Params(6)                                           # @assert 1 <= k <= 5, src/fhe2.jl:39

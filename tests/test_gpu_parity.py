@@ -255,3 +255,20 @@ def test_chained_layers_match_oracle_p64(env64, so, sg):
         l1, l2, y1, y2 = ref[0], ref[2], want[0], want[2]
     last = sg.bootstrap_chain(bkey, lwes[:W], lwes[W:2 * W], layers)
     assert all(np.array_equal(a, b) for a, b in zip(last, got[-1]))
+
+
+@pytest.mark.parametrize("k", [1, 3, 5])
+def test_rns2_arithmetic_matches_oracle(so, sg, k):
+    """RNS2Number * + - (src/rns.jl:51-60) with the moduli of Scheme2.Params(k): random and edge operands"""
+    S2 = sg.Scheme2Params(k)
+    rng = np.random.default_rng(60 + k)
+    N = 1 << 16
+    a1 = rng.integers(0, S2.B, size=N, dtype=np.uint64); a2 = rng.integers(0, S2.Bp, size=N, dtype=np.uint64)
+    b1 = rng.integers(0, S2.B, size=N, dtype=np.uint64); b2 = rng.integers(0, S2.Bp, size=N, dtype=np.uint64)
+    for arr, M in ((a1, S2.B), (a2, S2.Bp), (b1, S2.B), (b2, S2.Bp)):
+        arr[:4] = (0, 1, M - 1, M - 2)
+    b1[:2] = (S2.B - 1, S2.B - 1); b2[:2] = (S2.Bp - 1, S2.Bp - 1)
+    for code, op in enumerate("*+-"):
+        g1, g2 = sg.rns2_op(op, (a1, a2), (b1, b2), S2.B, S2.Bp)
+        r1, r2 = so.rns2_op(code, a1, a2, b1, b2, S2.B, S2.Bp)
+        assert np.array_equal(g1, r1) and np.array_equal(g2, r2), op
