@@ -53,6 +53,17 @@ def int_peak_imad_per_s() -> tuple[float, str]:
         return 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1.965 GHz (fallback)"
 
 
+def ncu_dram_bytes_per_gate(n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one bootstrap_kernel launch (ncu --set full capture of a one-wave
+    launch at Params(1024), committed under profiles/), per gate; None for other parameter sets."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")) as f:
+            t = json.load(f)
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["gates_per_launch"] if n == 1024 else None
+    except Exception:
+        return None
+
+
 def hbm_peak_gbs() -> tuple[float, str]:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -304,13 +315,33 @@ def run_ours(args) -> None:
             "verified": verified,
             "key_setup_s": key_s,
             "roofline": {"bound": "int32-pipe", "achieved": per_gpu * imad_gate / 1e9, "peak": peak / 1e9, "unit": "GIMAD/s",
-                         "frac": per_gpu * imad_gate / peak, "traffic": None,
+                         "frac": per_gpu * imad_gate / peak,
+                         "traffic": (ncu_dram_bytes_per_gate(n) * batch) if ncu_dram_bytes_per_gate(n) else None,
+                         "traffic_note": "ncu DRAM bytes of a 148-gate launch (profiles/ncu_r01_traffic.json) scaled to this batch; "
+                                         "almost all of it is per-gate scratch written back from L2, not algorithmic bytes",
                          "kernel": "bootstrap_kernel (one launch = one step = batch gates x n fused accumulation steps)",
                          "algorithmic_imad_per_gate": imad_gate, "peak_source": peak_src,
                          "hbm": {"algorithmic_key_bytes_per_launch": key_bytes * waves,
                                  "achieved_gbs": key_bytes * waves / (dev_ms / args.steps / 1e3) / 1e9, "peak_gbs": hbm, "peak_source": hbm_src,
                                  "note": "key streamed once per wave of 148 lock-step gates; far below HBM peak by design (integer bound)"}},
         }
+        # second half of BASELINE.json's metric: standalone NTT polymuls/s at this ring degree (both operands full size)
+        try:
+            pb = 1024
+            pa = torch.from_numpy((np.random.default_rng(7).integers(0, 1 << 62, size=(pb, P.m, 2), dtype=np.uint64) &
+                                   np.array([0xFFFFFFFFFFFFFFFF, (1 << max(qbits - 65, 0)) - 1], np.uint64)).view(np.int64)).cuda()
+            po = torch.empty_like(pa)
+            for _ in range(3):
+                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pa.data_ptr(), po.data_ptr(), stream.cuda_stream))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pa.data_ptr(), po.data_ptr(), stream.cuda_stream))
+            e1.record(stream); torch.cuda.synchronize()
+            out["ntt_polymul"] = {"value": 5 * pb / (e0.elapsed_time(e1) / 1e3), "unit": "polymuls/s",
+                                  "workload": f"negacyclic products in Z_Q[x]/(x^{P.m}+1), batch {pb}, both operands {qbits}-bit (sgfhe_polymul_device)"}
+        except Exception as ex:  # the headline number must not depend on the secondary one
+            out["ntt_polymul"] = {"error": str(ex)}
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_gates_per_s(n, args.cpu_seconds)
         print(json.dumps(out))

@@ -779,17 +779,18 @@ __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_
 
 
 // ---- Scheme 2 element type (src/rns.jl:8-60): limb-wise arithmetic on (v mod M1, v mod M2), M < 2^48 ------------
-__device__ __forceinline__ uint64_t mulmod48(uint64_t a, uint64_t b, uint64_t M, double Minv) {
-  const uint64_t q = (uint64_t)((double)a * (double)b * Minv);      // within 1 of floor(a b / M)
-  int64_t r = (int64_t)(a * b - q * M);                              // exact modulo 2^64, true value in (-M, 2M)
-  if (r < 0) r += (int64_t)M;
-  if (r >= (int64_t)M) r -= (int64_t)M;
-  return (uint64_t)r;
+// Barrett: mu = floor(2^96 / M), 2^32 < M < 2^48;  a, b < M
+__device__ __forceinline__ uint64_t mulmod48(uint64_t a, uint64_t b, uint64_t M, uint64_t mu) {
+  const uint64_t lo = a * b, hi = __umul64hi(a, b);
+  const uint64_t q = __umul64hi((hi << 32) | (lo >> 32), mu);          // in [ab/M - 2, ab/M]
+  uint64_t r = lo - q * M;                                             // exact modulo 2^64, true value in [0, 3M)
+  r = r >= M ? r - M : r;
+  r = r >= M ? r - M : r;
+  return r;
 }
 __global__ void rns2_kernel(int op, size_t count, const uint64_t* __restrict__ a1, const uint64_t* __restrict__ a2,
                             const uint64_t* __restrict__ b1, const uint64_t* __restrict__ b2, uint64_t M1, uint64_t M2,
-                            uint64_t* __restrict__ o1, uint64_t* __restrict__ o2) {
-  const double i1 = 1.0 / (double)M1, i2 = 1.0 / (double)M2;
+                            uint64_t i1, uint64_t i2, uint64_t* __restrict__ o1, uint64_t* __restrict__ o2) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     const uint64_t x1 = a1[i], x2 = a2[i], y1 = b1[i], y2 = b2[i];
     uint64_t r1, r2;
@@ -1323,17 +1324,19 @@ extern "C" int sgfhe_rns2_op_device(int32_t device, int32_t op, uint64_t count, 
                                     uint64_t* d_o2, void* stream) {
   if (!d_a1 || !d_a2 || !d_b1 || !d_b2 || !d_o1 || !d_o2) return fail(SGFHE_ERR_ARG, "NULL argument");
   if (op < 0 || op > 2) return fail(SGFHE_ERR_ARG, "op must be 0 (*), 1 (+) or 2 (-)");
-  if (M1 < 2 || M2 < 2 || M1 >= ((uint64_t)1 << 48) || M2 >= ((uint64_t)1 << 48)) return fail(SGFHE_ERR_ARG, "moduli must be below 2^48");
+  if (M1 <= ((uint64_t)1 << 32) || M2 <= ((uint64_t)1 << 32) || M1 >= ((uint64_t)1 << 48) || M2 >= ((uint64_t)1 << 48))
+    return fail(SGFHE_ERR_ARG, "moduli must be in (2^32, 2^48) (the range of Scheme2.Params(1..5))");
   if (count == 0) return SGFHE_OK;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SGFHE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
   CK(cudaSetDevice(device));
-  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int threads = 256;
   size_t blocks = (count + threads - 1) / threads;
-  const size_t cap = (size_t)prop.multiProcessorCount * 8;
+  const size_t cap = (size_t)sms * 8;
   if (blocks > cap) blocks = cap;
-  rns2_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(op, count, d_a1, d_a2, d_b1, d_b2, M1, M2, d_o1, d_o2);
+  const uint64_t mu1 = (uint64_t)((((u128)1) << 96) / M1), mu2 = (uint64_t)((((u128)1) << 96) / M2);
+  rns2_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(op, count, d_a1, d_a2, d_b1, d_b2, M1, M2, mu1, mu2, d_o1, d_o2);
   ++g_launches;
   CK(cudaGetLastError());
   return SGFHE_OK;
