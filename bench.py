@@ -350,6 +350,66 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+def run_depth(args) -> None:
+    """BASELINE.json configs[4]: examples/depth.jl -- `layers` sequential gate layers at Params(512), `batch` independent
+    bit pairs per layer and GPU, layer l+1 bootstrapping (AND_l, XOR_l); ciphertexts stay in HBM between layers."""
+    import torch
+    import sgfhe_jl_b200 as sg
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, W, layers = args.n, args.batch, args.layers
+    P = sg.Params(n, device=local)
+    sk = sg.PrivateKey(P, np.random.default_rng([args.seed, 1]))
+    if rank == 0:
+        bkey = sg.BootstrapKey(np.random.default_rng([args.seed, 2]), sk)
+        bkey.upload()
+    else:
+        bkey = sg.BootstrapKey(params=P, key=np.zeros((0, 4, 2, P.m, 2), np.uint64))
+        bkey._uploaded = True
+    if world > 1:
+        sg.broadcast_key(P, n, dist)
+    rng = np.random.default_rng([args.seed, 3, rank])
+    bits, lw = [], []
+    for _ in range((2 * W + n - 1) // n):
+        msg = rng.integers(0, 2, size=n, dtype=np.uint8)
+        lw.append(np.stack([e.lwe.flat() for e in sg.split_ciphertext(sg.encrypt(sk, rng, msg))])); bits.append(msg)
+    bits = np.concatenate(bits)[: 2 * W]; lw = np.concatenate(lw)[: 2 * W]
+    for _ in range(args.warmup):
+        sg.bootstrap_chain(bkey, lw[:W], lw[W:], 1)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outs = sg.bootstrap_chain(bkey, lw[:W], lw[W:], layers)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    y1, y2 = bits[:W].astype(np.int64), bits[W:].astype(np.int64)
+    for _ in range(layers):
+        y1, y2 = y1 & y2, y1 ^ y2                                   # depth.jl:71-75
+    skb = sk.key.astype(bool)
+    b1 = (outs[0][:, n].astype(np.int64) - outs[0][:, :n][:, skb].astype(np.int64).sum(axis=1)) % P.r
+    ok = bool(np.array_equal(((b1 + P.Dr // 2) % P.r) // P.Dr, y1))
+    t = torch.tensor([dt, 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        dt = float(t[0])
+        print(json.dumps({"metric": METRIC, "value": W * layers * world * args.steps / dt, "unit": UNIT, "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u32 (RNS residues of Z_Q, exact)", "data": "synthetic",
+                          "config": {"workload": f"examples/depth.jl chain at Params({n}): {layers} sequential layers x {W} gates per GPU, "
+                                                 "(AND, XOR) fed back in, ciphertexts resident in HBM", "n": n, "batch_per_gpu": W, "layers": layers},
+                          "verified": bool(float(t[1]) == 0.0)}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -361,7 +421,12 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--workload", default="gates", choices=["gates", "depth"], help="depth = BASELINE configs[4] (use --n 512 --batch W --layers L)")
+    ap.add_argument("--layers", type=int, default=100)
     args = ap.parse_args()
+    if args.workload == "depth" and args.impl == "ours":
+        run_depth(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
