@@ -272,3 +272,42 @@ def test_rns2_arithmetic_matches_oracle(so, sg, k):
         g1, g2 = sg.rns2_op(op, (a1, a2), (b1, b2), S2.B, S2.Bp)
         r1, r2 = so.rns2_op(code, a1, a2, b1, b2, S2.B, S2.Bp)
         assert np.array_equal(g1, r1) and np.array_equal(g2, r2), op
+
+
+def test_error_behaviour_and_empty_batch(sg, so):
+    """boundary errors: no key, truncated key, bad shapes, empty batch"""
+    P, OP = sg.Params(64), so.Params(64)
+    sk = so.make_secret(OP, 0)
+    _, lwes = so.make_lwes(OP, sk, 0)
+    part = sg.BootstrapKey(params=P, key=so.make_bkey(OP, sk, 0, rows=3))
+    with pytest.raises(sg.SgfheError, match="no complete bootstrap key"):
+        sg.bootstrap_batch(part, None, lwes[:2], lwes[2:4])            # only 3 of n rows uploaded
+    with pytest.raises(sg.SgfheError):
+        sg.bootstrap_trace(part, None, lwes[0], lwes[1], n_steps=4)    # more steps than rows
+    with pytest.raises(sg.SgfheError, match=r"\[batch, n\+1\]"):
+        sg.bootstrap_batch(part, None, lwes[:2, :-1], lwes[2:4, :-1])
+    full = sg.BootstrapKey(params=P, key=so.make_bkey(OP, sk, 0))
+    outs = sg.bootstrap_batch(full, None, lwes[:0], lwes[:0])
+    assert all(o.shape == (0, OP.n + 1) for o in outs)
+    P.close()
+
+
+def test_full_gates_paper_size(so, sg):
+    """Params(1024), full n = 1024 steps with a real key: 2 gates equal the oracle bit for bit, 12 more decrypt to
+    the plaintext gates (the 4096-gate batch of BASELINE.json is checked the same way inside bench.py)."""
+    P, OP = sg.Params(1024), so.Params(1024)
+    so.set_setup_threads(16)
+    sk = so.make_secret(OP, 1)
+    key = so.make_bkey(OP, sk, 1)
+    bits, lwes = so.make_lwes(OP, sk, 1)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    G = 14
+    l1, l2 = lwes[:G], lwes[G:2 * G]
+    outs = sg.bootstrap_batch(bkey, None, l1, l2)
+    ref = so.bootstrap_batch(OP, key, l1[:2], l2[:2], literal=False, threads=2)
+    for o, r in zip(outs, ref):
+        assert np.array_equal(o[:2], r)
+    for g in range(G):
+        y1, y2 = int(bits[g]), int(bits[G + g])
+        assert tuple(so.decrypt_lwe(OP, sk, o[g]) for o in outs) == (y1 & y2, y1 | y2, y1 ^ y2)
+    P.close()
