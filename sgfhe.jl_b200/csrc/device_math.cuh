@@ -31,6 +31,7 @@ struct DevConst {
   uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP], vk[MAXP];
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
+  uint64_t mu64[MAXP];                      // floor(2^64 / p)
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
   uint32_t dig_negc[MAXP];                  // p - (2^46 mod p)
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
@@ -310,8 +311,11 @@ __device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t
 // canonical value of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p)
 __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c) {
   const uint32_t p = C.p[i];
+  // c = c2 2^64 + c1 2^32 + c0  ->  t = c2 (2^64 mod p) + c1 (2^32 mod p) + c0 < 2^63, then Barrett with mu = floor(2^64 / p)
   const uint64_t t = (uint64_t)(uint32_t)(c >> 64) * C.r64[i] + (uint64_t)(uint32_t)(c >> 32) * C.r32[i] + (uint32_t)c;
-  uint32_t r = (uint32_t)(t % p);
+  const uint64_t q = __umul64hi(t, C.mu64[i]);                      // in [t/p - 1, t/p]
+  uint32_t r = (uint32_t)(t - q * p);                               // in [0, 2p)
+  r = csub(r, p);
   if (c > (C.Q >> 1)) r = r >= C.qmodp[i] ? r - C.qmodp[i] : r + p - C.qmodp[i];
   return r;
 }

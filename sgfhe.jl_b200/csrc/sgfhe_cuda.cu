@@ -873,6 +873,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     dc->r32[i] = (uint32_t)(((uint64_t)1 << 32) % p);
     dc->r64[i] = (uint32_t)((((u128)1) << 64) % p);
     dc->qmodp[i] = (uint32_t)(hp.Q % p);
+    dc->mu64[i] = (uint64_t)((((u128)1) << 64) / p);
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
     dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p);
