@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsgfhe_cuda.so")
+SO_PATH = os.environ.get("SGFHE_CUDA_LIB") or os.path.join(_HERE, "libsgfhe_cuda.so")   # override: A/B builds only
 _LIB = None
 
 # every symbol include/sgfhe_cuda.h declares

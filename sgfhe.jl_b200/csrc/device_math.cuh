@@ -35,6 +35,7 @@ struct DevConst {
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
   uint32_t dig_negc[MAXP];                  // p - (2^46 mod p)
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
+  uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t crt_c[2][MAXP][3];               // (P/p_i) mod Q, 32-bit limbs
   uint32_t negP[2][3];                      // (-P) mod Q
 };
@@ -128,6 +129,20 @@ __device__ __forceinline__ void stage_table(void* dst, const void* src, uint32_t
   constexpr uint32_t CH = 16384;
   for (uint32_t o = 0; o < bytes; o += CH)
     bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o < CH ? bytes - o : CH, bar);
+}
+
+// inverse block without its last level (l = 0, pairs (k, k + R/2)): the caller folds a scaling into that level
+template <int LOGR>
+__device__ __forceinline__ void inv_block_upper(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {
+  constexpr int R = 1 << LOGR;
+#pragma unroll
+  for (int l = LOGR - 1; l >= 1; --l) {
+    const int half = R >> (l + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << l); ++g)
+#pragma unroll
+      for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
+  }
 }
 
 // Compile-time shape of the on-chip transform of length M = 2^LOGM.

@@ -570,16 +570,21 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(3);
     // ---- top inverse stages in registers + CRT pre-scaling + store of the residues --------------------------
+    // last level: x' = (x + y) s, y' = (x - y) psi^(-m/2) s with s = m^-1 (P/p)^-1 folded into both multiplications
     {
-      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i];
+      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i], sw = C.scale_w[i], sws = C.scale_w_sh[i];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t x[R0];
 #pragma unroll
         for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
-        inv_block<LR0>(x, top + R0, p, p2, z);
+        inv_block_upper<LR0>(x, top + R0, p, p2, z);
 #pragma unroll
-        for (int k = 0; k < R0; ++k) S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(x[k], sc, scs, p), p);
+        for (int k = 0; k < R0 / 2; ++k) {
+          const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
+          S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(s0, sc, scs, p), p);
+          S.zres[((size_t)i * 2 + c) * m + tid + (k + R0 / 2) * T] = csub(shoup_mul(d0, sw, sws, p), p);
+        }
       }
     }
     SGFHE_TICK(4);
@@ -892,6 +897,11 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       if (basis == 1) sc = h_mulmod64(sc, dc->r32[i], p);
       dc->scale[basis][i] = (uint32_t)sc;
       dc->scale_sh[basis][i] = (uint32_t)((sc << 32) / p);
+      if (basis == 0) {                                   // psi^(-m/2) = (psi^-1)^(m/2)
+        const uint64_t psi_inv = h_powmod64(h_root_2m(p, hp.m), p - 2, p);
+        const uint64_t sw = h_mulmod64(sc, h_powmod64(psi_inv, hp.m / 2, p), p);
+        dc->scale_w[i] = (uint32_t)sw; dc->scale_w_sh[i] = (uint32_t)((sw << 32) / p);
+      }
     }
   }
   const int m = hp.m;
