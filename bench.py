@@ -271,7 +271,11 @@ def run_ours(args) -> None:
     clocks = sampler.stop() if rank == 0 else None
     # e2e: host buffers through the public C ABI; wall clock brackets H2D + kernel + D2H (call is synchronous)
     step_host()
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
     _, e2e_wall = timed(step_host, args.steps)
+    clocks_e2e = sampler2.stop() if rank == 0 else None
     t = torch.tensor([dev_ms, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,6 +316,7 @@ def run_ours(args) -> None:
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * h1.numel() * 8), "d2h_bytes_per_step": int(3 * h1.numel() * 8)},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "clocks_e2e": clocks_e2e,
             "verified": verified,
             "key_setup_s": key_s,
             "roofline": {"bound": "int32-pipe", "achieved": per_gpu * imad_gate / 1e9, "peak": peak / 1e9, "unit": "GIMAD/s",

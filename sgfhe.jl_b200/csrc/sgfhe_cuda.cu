@@ -836,6 +836,7 @@ struct sgfhe_ctx {
   uint32_t* d_keyhat = nullptr; int key_rows = 0; size_t keyhat_capacity_rows = 0;
   uint8_t* d_scratch = nullptr; int scratch_ctas = 0;
   uint32_t* d_pm_scratch = nullptr; int pm_ctas = 0;
+  uint64_t* d_io = nullptr; size_t io_capacity = 0;
 };
 
 static void to_limbs(u128 v, uint32_t out[3]) { out[0] = (uint32_t)v; out[1] = (uint32_t)(v >> 32); out[2] = (uint32_t)(v >> 64); }
@@ -1061,7 +1062,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
 extern "C" int sgfhe_ctx_destroy(sgfhe_ctx* c) {
   if (!c) return SGFHE_OK;
   cudaSetDevice(c->device);
-  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch);
+  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch); cudaFree(c->d_io);
   delete c;
   return SGFHE_OK;
 }
@@ -1187,22 +1188,25 @@ extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t
   CK(cudaSetDevice(c->device));
   const size_t lwe_bytes = (size_t)batch * (c->hp.n + 1) * sizeof(uint64_t);
   const size_t draw_bytes = draws ? (size_t)batch * c->hp.n * 4 * c->hp.m * sizeof(int64_t) : 0;
-  uint64_t* d_io = nullptr; int64_t* d_draws = nullptr;
-  if (cudaMalloc(&d_io, 5 * lwe_bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of LWE buffers failed");
-  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) { cudaFree(d_io); return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed"); }
+  if (5 * lwe_bytes > c->io_capacity) {                 // LWE staging buffers are kept between calls (grow only)
+    cudaFree(c->d_io); c->d_io = nullptr; c->io_capacity = 0;
+    if (cudaMalloc(&c->d_io, 5 * lwe_bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of LWE buffers failed");
+    c->io_capacity = 5 * lwe_bytes;
+  }
+  uint64_t* d_io = c->d_io; int64_t* d_draws = nullptr;
+  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed");
   const size_t w = lwe_bytes / sizeof(uint64_t);
   int rc = SGFHE_OK;
-  cudaError_t e = cudaMemcpy(d_io, lwe1, lwe_bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_io + w, lwe2, lwe_bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    rc = sgfhe_bootstrap_batch_device(c, batch, d_io, d_io + w, d_draws, d_io + 2 * w, d_io + 3 * w, d_io + 4 * w, nullptr);
-    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
-  }
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_and, d_io + 2 * w, lwe_bytes, cudaMemcpyDeviceToHost);
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_or, d_io + 3 * w, lwe_bytes, cudaMemcpyDeviceToHost);
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_xor, d_io + 4 * w, lwe_bytes, cudaMemcpyDeviceToHost);
-  cudaFree(d_io); cudaFree(d_draws);
+  cudaError_t e = cudaMemcpyAsync(d_io, lwe1, lwe_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_io + w, lwe2, lwe_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws) e = cudaMemcpyAsync(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = sgfhe_bootstrap_batch_device(c, batch, d_io, d_io + w, d_draws, d_io + 2 * w, d_io + 3 * w, d_io + 4 * w, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_and, d_io + 2 * w, lwe_bytes, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_or, d_io + 3 * w, lwe_bytes, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_xor, d_io + 4 * w, lwe_bytes, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
+  cudaFree(d_draws);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_batch: ") + cudaGetErrorString(e));
   return SGFHE_OK;
