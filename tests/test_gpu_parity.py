@@ -170,9 +170,10 @@ def test_public_api_roundtrip_p64(sg):
     P.close()
 
 
-@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("n", [128, 256, 512, 1024])
 def test_bootstrap_trace_truncated_large(so, sg, n):
-    """paper-size parameters (86-bit Q, m = 8192): first steps of the loop against the oracle, both modes"""
+    """every supported transform shape (m = 1024 ... 8192; 86-bit Q at n = 1024): first steps of the loop against the
+    oracle, both flatten modes"""
     P, OP = sg.Params(n), so.Params(n)
     steps = 3
     sk = so.make_secret(OP, 1)
