@@ -388,6 +388,14 @@ struct Shape4 {
 
 __device__ __forceinline__ uint2 tw_neg(uint2 w, uint32_t p) { return make_uint2(p - w.x, ~w.y); }
 
+// Between the top stages and the last inverse pass every element with index bits [9, LOGM) fixed is touched only by
+// the 64 consecutive threads that own that 512-element slice, so the stride-64 <-> stride-8 hand-over needs a
+// named barrier over those two warps only (ids 1..8), and warp pairs drift apart: some stream key words from L2 in
+// the fused phase while others run butterflies.
+__device__ __forceinline__ void group_bar64() {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");
+}
+
 // twiddles of one radix-8 block from the staged forward table; inverse ones are mirrored and negated
 template <bool FWD>
 __device__ __forceinline__ void block_twiddles(const uint2* tab, int lvl, int g, uint32_t p, uint2 (&w)[7]) {
@@ -488,7 +496,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
     SGFHE_TICK(0);
     pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
-    __syncthreads();
+    group_bar64();                                       // bits [0,9) stay inside groups of 64 consecutive threads
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
     {                                                    // the first set is requested before the stride-8 pass
@@ -556,7 +564,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     __syncwarp();
     SGFHE_TICK(2);
     pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
-    __syncthreads();
+    group_bar64();
     pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
     __syncthreads();                                     // last reader of `tab` for this prime is done
     {
