@@ -123,6 +123,13 @@ int sgfhe_flatten_poly(sgfhe_ctx* ctx, const uint64_t* a, const int64_t* draws, 
 int sgfhe_external_product(sgfhe_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* A,
                            const int64_t* draws, uint64_t* a_out, uint64_t* b_out);
 
+/* Serialisation of the pre-transformed key (the reference has none: `Serialization` is imported and unused at
+ * examples/test_scheme2.jl:3).  The blob carries n, m, Q and the RNS basis and is rejected by a context of other
+ * parameters.  export_size -> export into a caller buffer; import replaces sgfhe_bkey_upload. */
+int sgfhe_bkey_export_size(sgfhe_ctx* ctx, int32_t rows, uint64_t* bytes);
+int sgfhe_bkey_export(sgfhe_ctx* ctx, int32_t rows, void* blob, uint64_t bytes);
+int sgfhe_bkey_import(sgfhe_ctx* ctx, const void* blob, uint64_t bytes);
+
 /* Scheme 2 (src/fhe2.jl, "experimental, not finished" upstream: it defines Params, keys, encrypt/decrypt and NO
  * bootstrap).  What exists upstream and is mirrored here: Params(k) (src/fhe2.jl:36-70) and the arithmetic of
  * its ring element type RNS2Number{UInt64, B, Bp} (src/rns.jl:51-60), batched. */

@@ -21,6 +21,7 @@ SYMBOLS = [
     "sgfhe_launch_count", "sgfhe_bkey_device_buffer", "sgfhe_bkey_adopt",
     "sgfhe_bootstrap_internal_batch", "sgfhe_shortened_products",
     "sgfhe_scheme2_params_derive", "sgfhe_rns2_op", "sgfhe_rns2_op_device",
+    "sgfhe_bkey_export_size", "sgfhe_bkey_export", "sgfhe_bkey_import",
 ]
 
 
@@ -67,6 +68,9 @@ def lib():
         L.sgfhe_bkey_adopt.argtypes = [vp, i32]
         L.sgfhe_bootstrap_internal_batch.argtypes = [vp, i32, u64p, u64p, vp, u64p, u64p, u64p]
         L.sgfhe_shortened_products.argtypes = [vp, i32, u64p, vp, u64p]
+        L.sgfhe_bkey_export_size.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
+        L.sgfhe_bkey_export.argtypes = [vp, i32, vp, C.c_uint64]
+        L.sgfhe_bkey_import.argtypes = [vp, vp, C.c_uint64]
         L.sgfhe_scheme2_params_derive.argtypes = [i32, C.POINTER(Scheme2ParamsC)]
         L.sgfhe_rns2_op.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p]
         L.sgfhe_rns2_op_device.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, vp]

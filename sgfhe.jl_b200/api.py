@@ -250,6 +250,26 @@ class BootstrapKey:
                             cell[0], cell[1] = v & 0xFFFFFFFFFFFFFFFF, v >> 64
         self._uploaded = False
 
+    def save_transformed(self, path: str):
+        """Write the pre-transformed (device) key to `path`; reload with BootstrapKey.load_transformed."""
+        self.upload()
+        L = _lib.lib()
+        rows = self.key.shape[0] if self.key is not None else self.params.n
+        nbytes = C.c_uint64()
+        check(L.sgfhe_bkey_export_size(self.params.ctx, rows, C.byref(nbytes)))
+        buf = np.empty(nbytes.value, np.uint8)
+        check(L.sgfhe_bkey_export(self.params.ctx, rows, _ptr(buf), nbytes.value))
+        buf.tofile(path)
+
+    @classmethod
+    def load_transformed(cls, params: "Params", path: str) -> "BootstrapKey":
+        """A key usable for bootstrap straight from a file written by save_transformed (no coefficient form kept)."""
+        buf = np.fromfile(path, np.uint8)
+        check(_lib.lib().sgfhe_bkey_import(params.ctx, _ptr(buf), buf.size))
+        bk = cls(params=params, key=np.zeros((0, 4, 2, params.m, 2), np.uint64))
+        bk._uploaded = True
+        return bk
+
     def upload(self):
         if not self._uploaded:
             check(_lib.lib().sgfhe_bkey_upload(self.params.ctx, _ptr(self.key), self.key.shape[0]))

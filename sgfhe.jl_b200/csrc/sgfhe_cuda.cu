@@ -1149,6 +1149,49 @@ extern "C" int sgfhe_bkey_adopt(sgfhe_ctx* c, int32_t rows) {
   return SGFHE_OK;
 }
 
+
+// Serialised form of the pre-transformed key: header + raw words, so a key is transformed once and reloaded later.
+struct KeyBlobHeader { uint32_t magic, version; int32_t n, m, L, rows; uint32_t p[MAXP]; uint64_t Q[2]; };
+static const uint32_t KEY_MAGIC = 0x53474B31u;   // "SGK1"
+
+extern "C" int sgfhe_bkey_export_size(sgfhe_ctx* c, int32_t rows, uint64_t* bytes) {
+  if (!c || !bytes) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (rows < 1 || rows > c->key_rows) return fail(SGFHE_ERR_STATE, "rows exceeds the uploaded key rows");
+  *bytes = sizeof(KeyBlobHeader) + (uint64_t)rows * keyhat_row_words(c) * sizeof(uint32_t);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_export(sgfhe_ctx* c, int32_t rows, void* blob, uint64_t bytes) {
+  uint64_t need = 0;
+  int rc = sgfhe_bkey_export_size(c, rows, &need); if (rc) return rc;
+  if (!blob || bytes < need) return fail(SGFHE_ERR_ARG, "blob buffer too small");
+  CK(cudaSetDevice(c->device));
+  KeyBlobHeader h; memset(&h, 0, sizeof h);
+  h.magic = KEY_MAGIC; h.version = 1; h.n = c->hp.n; h.m = c->hp.m; h.L = c->dc.L; h.rows = rows;
+  for (int i = 0; i < MAXP; ++i) h.p[i] = c->dc.p[i];
+  h.Q[0] = (uint64_t)c->hp.Q; h.Q[1] = (uint64_t)(c->hp.Q >> 64);
+  memcpy(blob, &h, sizeof h);
+  CK(cudaMemcpy(static_cast<char*>(blob) + sizeof h, c->d_keyhat, need - sizeof h, cudaMemcpyDeviceToHost));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_import(sgfhe_ctx* c, const void* blob, uint64_t bytes) {
+  if (!c || !blob || bytes < sizeof(KeyBlobHeader)) return fail(SGFHE_ERR_ARG, "bad blob");
+  KeyBlobHeader h; memcpy(&h, blob, sizeof h);
+  if (h.magic != KEY_MAGIC || h.version != 1) return fail(SGFHE_ERR_ARG, "not a serialised sgfhe key");
+  if (h.n != c->hp.n || h.m != c->hp.m || h.L != c->dc.L || h.Q[0] != (uint64_t)c->hp.Q || h.Q[1] != (uint64_t)(c->hp.Q >> 64))
+    return fail(SGFHE_ERR_ARG, "serialised key belongs to other parameters");
+  for (int i = 0; i < h.L; ++i) if (h.p[i] != c->dc.p[i]) return fail(SGFHE_ERR_ARG, "serialised key uses another RNS basis");
+  if (h.rows < 1 || h.rows > c->hp.n) return fail(SGFHE_ERR_ARG, "bad row count");
+  const uint64_t need = sizeof h + (uint64_t)h.rows * keyhat_row_words(c) * sizeof(uint32_t);
+  if (bytes < need) return fail(SGFHE_ERR_ARG, "truncated blob");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_keyhat(c, h.rows); if (rc) return rc;
+  CK(cudaMemcpy(c->d_keyhat, static_cast<const char*>(blob) + sizeof h, need - sizeof h, cudaMemcpyHostToDevice));
+  c->key_rows = h.rows;
+  return SGFHE_OK;
+}
+
 static int launch_gates(sgfhe_ctx* c, GateArgs& A, cudaStream_t st) {
   const int grid = A.batch < c->max_ctas ? A.batch : c->max_ctas;
   int rc = ensure_scratch(c, grid); if (rc) return rc;

@@ -312,3 +312,19 @@ def test_full_gates_paper_size(so, sg):
         y1, y2 = int(bits[g]), int(bits[G + g])
         assert tuple(so.decrypt_lwe(OP, sk, o[g]) for o in outs) == (y1 & y2, y1 | y2, y1 ^ y2)
     P.close()
+
+
+def test_transformed_key_roundtrip(env64, sg, tmp_path):
+    """serialise the pre-transformed key, load it into a fresh context, same ciphertexts out; wrong parameters rejected"""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    ref = sg.bootstrap_batch(bkey, None, lwes[:3], lwes[3:6])
+    path = str(tmp_path / "key.sgk")
+    bkey.save_transformed(path)
+    P2 = sg.Params(64)
+    bk2 = sg.BootstrapKey.load_transformed(P2, path)
+    got = sg.bootstrap_batch(bk2, None, lwes[:3], lwes[3:6])
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    P3 = sg.Params(128)
+    with pytest.raises(sg.SgfheError, match="other parameters"):
+        sg.BootstrapKey.load_transformed(P3, path)
+    P2.close(); P3.close()
