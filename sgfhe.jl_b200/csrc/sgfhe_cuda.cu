@@ -395,6 +395,19 @@ __device__ __forceinline__ uint2 tw_neg(uint2 w, uint32_t p) { return make_uint2
 __device__ __forceinline__ void group_bar64() {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");
 }
+// With two radix-8 blocks per thread and polynomial (m = 8192) each WARP owns one 512-element slice outright (blocks
+// lane and lane + 32 of slice warp_id), so the three shared-memory passes and the fused phase between the top stages
+// exchange data inside a warp only: __syncwarp replaces the block-level barriers and the 16 warps drift freely
+// (tools/microbench/bfly2.cu: a barrier per pass costs 19-45 % of the butterfly throughput).
+template <int LOGM>
+__device__ __forceinline__ int block_of(int tid, int q) {
+  using S4 = Shape4<LOGM>;
+  return S4::NB == 2 ? (((tid >> 5) << 6) | (q << 5) | (tid & 31)) : tid + q * S4::T;
+}
+template <int LOGM>
+__device__ __forceinline__ void slice_sync() {
+  if (Shape4<LOGM>::NB == 2) __syncwarp(); else group_bar64();
+}
 
 // twiddles of one radix-8 block from the staged forward table; inverse ones are mirrored and negated
 template <bool FWD>
@@ -421,7 +434,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   const uint32_t p2 = 2 * p;
 #pragma unroll
   for (int q = 0; q < S4::NB; ++q) {
-    const int blk = threadIdx.x + q * S4::T;
+    const int blk = block_of<LOGM>(threadIdx.x, q);
     const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
     uint2 w[7];
     block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
@@ -496,13 +509,13 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
     SGFHE_TICK(0);
     pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
-    group_bar64();                                       // bits [0,9) stay inside groups of 64 consecutive threads
+    slice_sync<LOGM>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
     {                                                    // the first set is requested before the stride-8 pass
-      const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * tid);
+      const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * block_of<LOGM>(tid, 0));
       kq[0][0] = __ldg(k0); kq[0][1] = __ldg(k0 + 1);
-      const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * tid);
+      const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * block_of<LOGM>(tid, 0));
       kq[0][2] = __ldg(k1); kq[0][3] = __ldg(k1 + 1);
     }
     pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
@@ -513,7 +526,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
       const uint32_t pinv = C.pinv_neg[i];
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        const int blk = tid + q * T, base = 8 * blk;
+        const int blk = block_of<LOGM>(tid, q), base = 8 * blk;
         const int a0 = swz(base), a1 = a0 ^ 4;
         uint2 w[7];
         block_twiddles<true>(tab, m / 8, blk, p, w);
@@ -525,8 +538,8 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
           const int sidx = q * 4 + j;
           if (sidx + 1 < NB * 4) {                       // prefetch the next (block, poly) key words
             const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
-            const uint4* k0 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj) * m + 8 * (tid + nq * T));
-            const uint4* k1 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj + 1) * m + 8 * (tid + nq * T));
+            const uint4* k0 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj) * m + 8 * block_of<LOGM>(tid, nq));
+            const uint4* k1 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj + 1) * m + 8 * block_of<LOGM>(tid, nq));
             kq[(sidx + 1) & 1][0] = __ldg(k0); kq[(sidx + 1) & 1][1] = __ldg(k0 + 1);
             kq[(sidx + 1) & 1][2] = __ldg(k1); kq[(sidx + 1) & 1][3] = __ldg(k1 + 1);
           }
@@ -564,7 +577,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     __syncwarp();
     SGFHE_TICK(2);
     pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
-    group_bar64();
+    slice_sync<LOGM>();
     pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
     __syncthreads();                                     // last reader of `tab` for this prime is done
     {
