@@ -25,9 +25,11 @@ struct DevConst {
   uint32_t zero;                // always 0; a constant-bank operand ptxas cannot fold (forces 3-input IADD3 on the ALU pipe)
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
-  uint64_t barrett_mu;          // floor(2^(sbits+35) / Q)
-  double barrett_inv;           // 2^(sbits-29) / Q, rounded down and scaled by (1 - 2^-40)
+  uint64_t s46;                 // 2^46 - s: bias of the stored digit words minus the digit offset
+  double barrett_inv;           // 2^(sbits-16) / Q, scaled by (1 - 2^-40): never above the true value
+  double inv35;                 // 1/35 rounded up
   uint32_t Ql[3], offl[3];      // Q and offs as 32-bit limbs
+  uint32_t KQ[4];               // K Q with K = L 2^30 + L + 1: an upper bound of every unreduced CRT sum of the bootstrap basis
   uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP], vk[MAXP];
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
@@ -284,40 +286,46 @@ __device__ __forceinline__ u128 addmodQ(u128 a, u128 b, u128 Q) { u128 s = a + b
 __device__ __forceinline__ u128 submodQ(u128 a, u128 b, u128 Q) { return a >= b ? a - b : a + Q - b; }
 __device__ __forceinline__ u128 negmodQ(u128 a, u128 Q) { return a ? Q - a : (u128)0; }
 
-// flatten(nothing, a, Val(B), Val(2)) as signed digits (src/utils.jl:155-189); a in [0,Q)
-__device__ __forceinline__ void decompose_det(const DevConst& C, u96 a, u96 Q, int64_t& d0, int64_t& d1) {
-  u96 off; off.x0 = C.offl[0]; off.x1 = C.offl[1]; off.x2 = C.offl[2];
-  a = addmod96(a, off, Q);                        // a += offset             (src/utils.jl:179)
-  // divrem(a, B), B = 35 2^kB, 22 <= kB <= 38   (src/utils.jl:172)
+// The accumulator is kept in OFFSET FORM a + offs mod Q (offs = s (1 + B), src/utils.jl:169,179), so the
+// decomposition starts at the divrem.  flatten(nothing, a, Val(B), Val(2)) (src/utils.jl:155-189) on a_off = a + offs:
+// returns the biased digit words dp_i = u_i - s + 2^46.  KB = log2(B / 35) = 3 LOGM - 1 (B = 35 r^2 n, src/fhe.jl:87).
+template <int KB>
+__device__ __forceinline__ void decompose_off(const DevConst& C, u96 a, uint64_t& dp0, uint64_t& dp1) {
+  // divrem(a, B), B = 35 2^KB   (src/utils.jl:172);  t = a >> KB < 35^2 2^KB < 2^49
   const uint64_t lo64 = (uint64_t)a.x0 | ((uint64_t)a.x1 << 32);
   const uint64_t hi64 = (uint64_t)a.x1 | ((uint64_t)a.x2 << 32);
-  const uint64_t t = C.kB >= 32 ? (hi64 >> (C.kB - 32)) : ((lo64 >> C.kB) | ((uint64_t)a.x2 << (64 - C.kB)));
-  const uint64_t lo = lo64 & ((1ull << C.kB) - 1);
-  const uint64_t u1 = t / 35u;
-  const uint64_t u0 = ((t - u1 * 35u) << C.kB) | lo;
-  d0 = (int64_t)(u0 - C.s);                       // - s                     (src/utils.jl:183-185)
-  d1 = (int64_t)(u1 - C.s);
+  const uint64_t t = KB >= 32 ? (hi64 >> (KB - 32)) : ((lo64 >> KB) | ((uint64_t)a.x2 << (64 - KB)));
+  const uint64_t lo = lo64 & ((1ull << KB) - 1);
+  // u1 = floor(t / 35) on the idle FP64 pipe: (2^52 + t) - 2^52 = t exactly, then trunc(t * inv35 + 2^52) has
+  // floor(t inv35) = floor(t / 35) in its mantissa (t inv35 - t/35 < 2^-8 < 1/35)
+  const double td = __hiloint2double(0x43300000 | (int)(uint32_t)(t >> 32), (int)(uint32_t)t) - 4503599627370496.0;
+  const double qd = __fma_rz(td, C.inv35, 4503599627370496.0);
+  const uint32_t q_lo = (uint32_t)__double2loint(qd), q_hi = (uint32_t)__double2hiint(qd) & 0xFFFFFu;
+  const uint32_t rem = (uint32_t)t - 35u * q_lo;                    // < 35
+  const uint64_t u1 = (uint64_t)q_lo | ((uint64_t)q_hi << 32);
+  const uint64_t u0 = ((uint64_t)rem << KB) | lo;
+  dp0 = u0 + C.s46;                               // - s  (src/utils.jl:183-185), + 2^46 storage bias
+  dp1 = u1 + C.s46;
 }
 
-// flatten(rng, ...) (src/utils.jl:198-241): x0, x1 are the caller's draws
-__device__ __forceinline__ void decompose(const DevConst& C, u96 a, u96 Q, int64_t x0, int64_t x1, bool random,
-                                          int64_t& d0, int64_t& d1) {
-  if (random) {                                   // rand_a = a - x0 - x1 B   (src/utils.jl:222,232-233)
-    i128 X = (i128)x1 * (i128)C.B + (i128)x0;
-    X %= (i128)C.Q;
-    if (X < 0) X += (i128)C.Q;
-    a = from128(submodQ(to128(a), (u128)X, C.Q));
-  }
-  decompose_det(C, a, Q, d0, d1);
-  d0 += x0;                                       // + x                     (src/utils.jl:236-238)
-  d1 += x1;
+// flatten(rng, ...) (src/utils.jl:198-241) on the offset form: x0, x1 are the caller's draws
+template <int KB>
+__device__ __forceinline__ void decompose_off_rand(const DevConst& C, u96 a, int64_t x0, int64_t x1, uint64_t& dp0, uint64_t& dp1) {
+  i128 X = (i128)x1 * (i128)C.B + (i128)x0;       // rand_a = a - x0 - x1 B   (src/utils.jl:222,232-233)
+  X %= (i128)C.Q;
+  if (X < 0) X += (i128)C.Q;
+  a = from128(submodQ(to128(a), (u128)X, C.Q));
+  decompose_off<KB>(C, a, dp0, dp1);
+  dp0 += (uint64_t)x0;                            // + x                     (src/utils.jl:236-238)
+  dp1 += (uint64_t)x1;
 }
+// canonical accumulator value <-> offset form
+__device__ __forceinline__ u96 off96(const DevConst& C) { u96 o; o.x0 = C.offl[0]; o.x1 = C.offl[1]; o.x2 = C.offl[2]; return o; }
+__device__ __forceinline__ u96 to_offset_form(const DevConst& C, u96 a) { return addmod96(a, off96(C), Q96(C)); }
+__device__ __forceinline__ u96 from_offset_form(const DevConst& C, u96 a) { return submod96(a, off96(C), Q96(C)); }
 
 // Signed digits (|d| < 2^46) are stored biased, dp = d + 2^46, as two words: lo = dp mod 2^32, hi = dp >> 18.
-__device__ __forceinline__ void digit_pack(int64_t d, uint32_t& lo, uint32_t& hi) {
-  const uint64_t dp = (uint64_t)(d + ((int64_t)1 << 46));
-  lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18);
-}
+__device__ __forceinline__ void digit_words(uint64_t dp, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18); }
 // residue of the digit mod p in [0,3p): mu = floor(2^50 / p), negc = p - (2^46 mod p)
 __device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t mu, uint32_t negc, uint32_t p) {
   return lo - __umulhi(hi, mu) * p + negc;
@@ -335,12 +343,25 @@ __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c
   return r;
 }
 
-// CRT lift: residues y_i = z (P/p_i)^-1 mod p_i of an integer |z| < P/32  ->  z mod Q, canonical.
-//   v = round(sum y_i / p_i) from the top 14 bits of each residue (error < 2^-11, margin 0.47);
-//   S = sum y_i c_i + v negP  (< 2^126);  z = S mod Q by a Barrett step whose quotient estimate is one
-//   double-precision multiply (the fp64 and conversion pipes are otherwise idle; the integer pipe is the bottleneck).
+// 128-bit limb helpers for the unreduced CRT sums
+__device__ __forceinline__ uint4 add128(uint4 a, uint4 b) {
+  uint4 r;
+  asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, %11;"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w));
+  return r;
+}
+__device__ __forceinline__ uint4 sub128(uint4 a, uint4 b) {
+  uint4 r;
+  asm("sub.cc.u32 %0, %4, %8;\n\tsubc.cc.u32 %1, %5, %9;\n\tsubc.cc.u32 %2, %6, %10;\n\tsubc.u32 %3, %7, %11;"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w));
+  return r;
+}
+
+// CRT sum: residues y_i = z (P/p_i)^-1 mod p_i (canonical) of an integer |z| < P/32  ->  S = sum y_i c_i + v negP, an
+// UNREDUCED representative of z mod Q with 0 <= S < (K 2^30 + K) Q, as four limbs.
+//   v = round(sum y_i / p_i) from the top 14 bits of each residue (error < 2^-11, margin 0.47).
 template <int BASIS, int K>
-__device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __restrict__ y, size_t stride) {
+__device__ __forceinline__ uint4 crt_sum(const DevConst& C, const uint32_t* __restrict__ y, size_t stride) {
   uint64_t colA[3] = {0, 0, 0}, colB[3] = {0, 0, 0};
   uint32_t vs = 0;
 #pragma unroll
@@ -357,36 +378,48 @@ __device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __res
 #pragma unroll
   for (int k = 0; k < 3; ++k) colB[k] += (uint64_t)v * C.negP[BASIS][k];
   // S = sum_k (colA[k] + colB[k]) 2^(32k) < 2^126, as four limbs
-  uint32_t s0, s1, s2, s3;
-  {
-    const uint64_t c0 = colA[0] + colB[0]; const uint32_t k0 = c0 < colA[0];
-    const uint64_t c1 = colA[1] + colB[1]; const uint32_t k1 = c1 < colA[1];
-    const uint64_t c2 = colA[2] + colB[2];                    // top column cannot overflow (c_i[2] < 2^29)
-    s0 = (uint32_t)c0;
-    const uint64_t t1 = (c0 >> 32) + (uint32_t)c1;
-    s1 = (uint32_t)t1;
-    const uint64_t t2 = (t1 >> 32) + (c1 >> 32) + k0 + (uint32_t)c2;
-    s2 = (uint32_t)t2;
-    s3 = (uint32_t)((t2 >> 32) + (c2 >> 32) + k1);
-  }
-  // quotient estimate qh in [S/Q - 3, S/Q]: T = floor(S / 2^(sbits-29)) < 2^63, qh = trunc(T * qinv), qinv ~ 2^(sbits-29)/Q biased down
-  const int sh = C.sbits - 29 - 32;                           // 0 <= sh < 32
-  const uint32_t tl = __funnelshift_r(s1, s2, sh), th = __funnelshift_r(s2, s3, sh);
-  const uint64_t qh = __double2ull_rz(__ull2double_rz((uint64_t)tl | ((uint64_t)th << 32)) * C.barrett_inv);
-  const uint32_t q0 = (uint32_t)qh, q1 = (uint32_t)(qh >> 32);
+  uint4 S;
+  const uint64_t c0 = colA[0] + colB[0]; const uint32_t k0 = c0 < colA[0];
+  const uint64_t c1 = colA[1] + colB[1]; const uint32_t k1 = c1 < colA[1];
+  const uint64_t c2 = colA[2] + colB[2];                      // top column cannot overflow (c_i[2] < 2^29)
+  S.x = (uint32_t)c0;
+  const uint64_t t1 = (c0 >> 32) + (uint32_t)c1;
+  S.y = (uint32_t)t1;
+  const uint64_t t2 = (t1 >> 32) + (c1 >> 32) + k0 + (uint32_t)c2;
+  S.z = (uint32_t)t2;
+  S.w = (uint32_t)((t2 >> 32) + (c2 >> 32) + k1);
+  return S;
+}
+
+// V mod Q for 0 <= V < 2^35 Q (four limbs); SB = bits(Q) - 1 = 6 LOGM + 8 (Q in [1220, 1225] r^4 n^2, src/fhe.jl:64-69).
+// Quotient estimate on the otherwise idle FP64 pipe, without integer<->double conversion instructions:
+//   T = floor(V / 2^(SB-16)) < 2^52 is placed in the mantissa of 2^52 + T, td = (2^52 + T) - 2^52 = T exactly, and
+//   trunc(td * barrett_inv + 2^52) carries qh = floor(T * barrett_inv) in its mantissa.  barrett_inv = 2^(SB-16)/Q (1 - 2^-40)
+//   never exceeds the true ratio, so floor(V/Q) - 1 <= qh <= floor(V/Q) and one conditional subtraction finishes.
+template <int SB>
+__device__ __forceinline__ u96 barrett96(const DevConst& C, uint4 V) {
+  constexpr int SH = SB - 16;                                 // 46 <= SH <= 70
+  uint32_t tl, th;
+  if constexpr (SH >= 64) { tl = __funnelshift_r(V.z, V.w, SH - 64); th = V.w >> (SH - 64); }
+  else { tl = __funnelshift_r(V.y, V.z, SH - 32); th = __funnelshift_r(V.z, V.w, SH - 32); }
+  const double td = __hiloint2double((int)(0x43300000u | th), (int)tl) - 4503599627370496.0;
+  const double qd = __fma_rz(td, C.barrett_inv, 4503599627370496.0);
+  const uint32_t q0 = (uint32_t)__double2loint(qd), q1 = (uint32_t)__double2hiint(qd) & 0xFFFFFu;
   const uint64_t m0 = (uint64_t)q0 * C.Ql[0];
   const uint64_t m1 = (uint64_t)q0 * C.Ql[1] + (m0 >> 32);
   const uint64_t m1b = (uint64_t)q1 * C.Ql[0] + (uint32_t)m1;
   u96 prod; prod.x0 = (uint32_t)m0; prod.x1 = (uint32_t)m1b;
   prod.x2 = q0 * C.Ql[2] + q1 * C.Ql[1] + (uint32_t)(m1 >> 32) + (uint32_t)(m1b >> 32);
-  u96 S; S.x0 = s0; S.x1 = s1; S.x2 = s2;
+  u96 S; S.x0 = V.x; S.x1 = V.y; S.x2 = V.z;
   uint32_t bw;
-  const u96 Q = Q96(C);
-  u96 R = sub96(S, prod, bw);                                 // exact mod 2^96; true value in [0, 4Q), 4Q < 2^96
-  R = csubQ(R, Q);
-  R = csubQ(R, Q);
-  R = csubQ(R, Q);
-  return R;
+  const u96 R = sub96(S, prod, bw);                           // exact mod 2^96; true value in [0, 2Q), 2Q < 2^96
+  return csubQ(R, Q96(C));
+}
+
+// CRT lift to the canonical residue mod Q (standalone products; the bootstrap path keeps the sums unreduced)
+template <int BASIS, int K, int SB>
+__device__ __forceinline__ u96 crt_lift(const DevConst& C, const uint32_t* __restrict__ y, size_t stride) {
+  return barrett96<SB>(C, crt_sum<BASIS, K>(C, y, stride));
 }
 
 // rescale(r, x, Q, round=true) with r = 2^logr (src/utils.jl:78-92 via reduce_modulus src/utils.jl:107-117)

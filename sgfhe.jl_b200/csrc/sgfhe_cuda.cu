@@ -40,6 +40,8 @@ struct GateArgs {
   int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
 
+// acc: the accumulator (a, b) in OFFSET FORM x + offs mod Q (device_math.cuh), limb-major; dig: the biased digit words
+// (dp mod 2^32, dp >> 18) of its gadget decomposition; zres: CRT-ready residues of the two product polynomials.
 struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; uint32_t* zres; };
 __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   Scratch s;
@@ -56,8 +58,9 @@ static size_t zres_bytes(int m, int L) { return (size_t)8 * L * m; }
 template <int LOGM>
 __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
   constexpr int m = 1 << LOGM;
-  const u96 DQ = from128(C.DQ), nDQ = from128(C.Q - C.DQ);
   u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
+  zero = to_offset_form(C, zero);
+  const u96 DQ = to_offset_form(C, from128(C.DQ)), nDQ = to_offset_form(C, from128(C.Q - C.DQ));
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     const int src = (int)((j + ub) & (uint64_t)(2 * m - 1));
     const int idx = src & (m - 1);
@@ -71,21 +74,68 @@ __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
 // gadget decomposition of accumulator polynomial c (src/utils.jl:253-264) into S.dig[2c], S.dig[2c+1]
 template <int LOGM>
 __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch& S, int c, const int64_t* __restrict__ draws) {
-  constexpr int m = 1 << LOGM;
-  const u96 Q = Q96(C);
+  constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1;
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     const u96 v = ld96(S.acc + c * 3 * m, m, idx);
-    int64_t d0, d1;
-    if (draws) decompose(C, v, Q, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], true, d0, d1);
-    else decompose_det(C, v, Q, d0, d1);
-    uint32_t lo, hi;
-    digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + idx] = lo; S.dighi[(2 * c) * m + idx] = hi;
-    digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + idx] = lo; S.dighi[(2 * c + 1) * m + idx] = hi;
+    uint64_t dp0, dp1;
+    if (draws) decompose_off_rand<KB>(C, v, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], dp0, dp1);
+    else decompose_off<KB>(C, v, dp0, dp1);
+    digit_words(dp0, S.diglo[(2 * c) * m + idx], S.dighi[(2 * c) * m + idx]);
+    digit_words(dp1, S.diglo[(2 * c + 1) * m + idx], S.dighi[(2 * c + 1) * m + idx]);
   }
 }
 
-// Phase C/D per accumulator polynomial: CRT lift into shared memory, then acc += x^u z - z
-// (mul_by_xj_minus_one, src/fhe.jl:554-556, applied to the product) fused with the next step's decomposition.
+// Phase D for one accumulator polynomial, branch-free per coefficient so that the D coefficients in flight interleave:
+//   EXT  (external-product seam): acc = z;   otherwise acc += x^u z - z  (mul_by_xj_minus_one, src/fhe.jl:554-556, applied
+//   to the product), evaluated on the unreduced CRT sums as V = acc + (KQ - S[j]) + (S[j-u] or KQ - S[j-u]) with ONE Barrett
+//   reduction; DEC: fused with the next step's gadget decomposition (RAND: with the caller's draws).
+template <int LOGM, int T, bool EXT, bool DEC, bool RAND>
+__device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S, const uint4* sm4, int c,
+                                            const int64_t* __restrict__ draws_next, int u) {
+  constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1, SB = 6 * LOGM + 8;
+  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
+  const int tid = threadIdx.x;
+  const uint4 KQ = make_uint4(C.KQ[0], C.KQ[1], C.KQ[2], C.KQ[3]);
+  const uint4 OFF = make_uint4(C.offl[0], C.offl[1], C.offl[2], 0);
+  uint32_t* acc = S.acc + c * 3 * m;
+  u96 aq[D];
+  if (!EXT) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) aq[d] = ld96(acc, m, tid + d * T);
+  }
+#pragma unroll 1
+  for (int it0 = 0; it0 < NIT; it0 += D) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int j = tid + (it0 + d) * T;
+      uint4 V;
+      if (EXT) {
+        V = add128(sm4[j], OFF);
+      } else {
+        const u96 a = aq[d];
+        if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
+        const int src = (j - u) & (2 * m - 1);
+        const uint4 zr = sm4[src & (m - 1)];
+        const uint4 nz = sub128(KQ, zr);                              // x^u z wraps with a sign flip
+        const bool neg = src >= m;
+        const uint4 zs = make_uint4(neg ? nz.x : zr.x, neg ? nz.y : zr.y, neg ? nz.z : zr.z, neg ? nz.w : zr.w);
+        V = add128(add128(make_uint4(a.x0, a.x1, a.x2, 0), sub128(KQ, sm4[j])), zs);   // < Q + 2 KQ < 2^35 Q
+      }
+      const u96 res = barrett96<SB>(C, V);
+      st96(acc, m, j, res);
+      if (DEC) {
+        uint64_t dp0, dp1;
+        if (RAND) decompose_off_rand<KB>(C, res, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], dp0, dp1);
+        else decompose_off<KB>(C, res, dp0, dp1);
+        digit_words(dp0, S.diglo[(2 * c) * m + j], S.dighi[(2 * c) * m + j]);
+        digit_words(dp1, S.diglo[(2 * c + 1) * m + j], S.dighi[(2 * c + 1) * m + j]);
+      }
+    }
+  }
+}
+
+// Phase C/D per accumulator polynomial: the UNREDUCED CRT sums S (four limbs each, device_math.cuh crt_sum) go to
+// shared memory, then update_poly.
 template <int LOGM, int T>
 __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
                                            const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
@@ -93,10 +143,10 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   constexpr int m = 1 << LOGM, L = Shape<LOGM>::L;
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
-  const u96 Q = Q96(C);
+  uint4* sm4 = reinterpret_cast<uint4*>(sm);                 // [m] sums: 16 m bytes = the four transform buffers
   // Both loops read data written a whole step ago (largely evicted to HBM): keep D iterations of loads in flight.
   constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
-  // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT lift runs
+  // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT sums run
   for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
   for (int c = 0; c < 2; ++c) {
@@ -119,45 +169,20 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
 #pragma unroll
             for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
           }
-          st96(sm, m, idx, crt_lift<0, L>(C, yc, 1));
+          sm4[idx] = crt_sum<0, L>(C, yc, 1);
         }
       }
     }
     __syncthreads();
     SGFHE_TICK(5);
-    uint32_t* acc = S.acc + c * 3 * m;
-    u96 aq[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) aq[d] = ld96(acc, m, tid + d * T);
-#pragma unroll 1
-    for (int it0 = 0; it0 < NIT; it0 += D) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int j = tid + (it0 + d) * T;
-        const u96 a = aq[d];
-        if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
-        const u96 z = ld96(sm, m, j);
-        u96 res;
-        if (ext) {
-          res = z;
-        } else {
-          const int src = (j - u) & (2 * m - 1);
-          u96 zr = ld96(sm, m, src & (m - 1));
-          uint32_t bw;
-          zr = sel96(src >= m, sub96(Q, zr, bw), zr);                 // -x^u z wraps with a sign flip; value in [0, Q]
-          res = add96(add96(a, sub96(Q, z, bw)), zr);                 // a + (Q - z) + zr  in [0, 3Q)
-          res = csubQ(csubQ(res, Q), Q);
-        }
-        st96(acc, m, j, res);
-        if (decompose_next) {
-          int64_t d0, d1;
-          if (draws_next) decompose(C, res, Q, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], true, d0, d1);
-          else decompose_det(C, res, Q, d0, d1);
-          uint32_t lo, hi;
-          digit_pack(d0, lo, hi); S.diglo[(2 * c) * m + j] = lo; S.dighi[(2 * c) * m + j] = hi;
-          digit_pack(d1, lo, hi); S.diglo[(2 * c + 1) * m + j] = lo; S.dighi[(2 * c + 1) * m + j] = hi;
-        }
-      }
+    if (ext) {
+      if (!decompose_next) update_poly<LOGM, T, true, false, false>(C, S, sm4, c, nullptr, u);
+      else if (draws_next) update_poly<LOGM, T, true, true, true>(C, S, sm4, c, draws_next, u);
+      else update_poly<LOGM, T, true, true, false>(C, S, sm4, c, nullptr, u);
+    } else {
+      if (!decompose_next) update_poly<LOGM, T, false, false, false>(C, S, sm4, c, nullptr, u);
+      else if (draws_next) update_poly<LOGM, T, false, true, true>(C, S, sm4, c, draws_next, u);
+      else update_poly<LOGM, T, false, true, false>(C, S, sm4, c, nullptr, u);
     }
     __syncthreads();
     SGFHE_TICK(6);
@@ -286,11 +311,11 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
   for (int k = threadIdx.x; k <= n; k += blockDim.x) {
     u128 va, vo;
     if (k < n) {
-      va = to128(ld96(S.acc, m, 3 * m / 4 - k));                           // extract(a, 3m/4+1, n)[k]
-      vo = negmodQ(to128(ld96(S.acc, m, m / 4 - k)), C.Q);                 // -extract(a, m/4+1, n)[k]
+      va = to128(from_offset_form(C, ld96(S.acc, m, 3 * m / 4 - k)));                           // extract(a, 3m/4+1, n)[k]
+      vo = negmodQ(to128(from_offset_form(C, ld96(S.acc, m, m / 4 - k))), C.Q);                 // -extract(a, m/4+1, n)[k]
     } else {
-      va = addmodQ(C.DQ, to128(ld96(S.acc + 3 * m, m, 3 * m / 4)), C.Q);   // DQ + b[3m/4]
-      vo = submodQ(C.DQ, to128(ld96(S.acc + 3 * m, m, m / 4)), C.Q);       // DQ - b[m/4]
+      va = addmodQ(C.DQ, to128(from_offset_form(C, ld96(S.acc + 3 * m, m, 3 * m / 4))), C.Q);   // DQ + b[3m/4]
+      vo = submodQ(C.DQ, to128(from_offset_form(C, ld96(S.acc + 3 * m, m, m / 4))), C.Q);       // DQ - b[m/4]
     }
     const u128 vx = submodQ(vo, va, C.Q);                                  // a_or - a_and
     if (raw) {
@@ -330,10 +355,11 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
     if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
     if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
       u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
+      zero = to_offset_form(C, zero);
       for (int e = threadIdx.x; e < m; e += blockDim.x) {
         const uint64_t* src = A.pack_in + ((size_t)g * m + e) * 2;
         u96 v; v.x0 = (uint32_t)src[0]; v.x1 = (uint32_t)(src[0] >> 32); v.x2 = (uint32_t)src[1];
-        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, v);
+        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, to_offset_form(C, v));
       }
     }
     __syncthreads();
@@ -353,7 +379,7 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
     if (A.trace) {
       uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
-        const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
+        const u96 v = from_offset_form(C, ld96(S.acc + (e / m) * 3 * m, m, e % m));
         tr[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); tr[2 * e + 1] = v.x2;
       }
     }
@@ -642,10 +668,11 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
     if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
       u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
+      zero = to_offset_form(C, zero);
       for (int e = threadIdx.x; e < m; e += blockDim.x) {
         const uint64_t* src = A.pack_in + ((size_t)g * m + e) * 2;
         u96 v; v.x0 = (uint32_t)src[0]; v.x1 = (uint32_t)(src[0] >> 32); v.x2 = (uint32_t)src[1];
-        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, v);
+        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, to_offset_form(C, v));
       }
     }
     __syncthreads();
@@ -665,7 +692,7 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     if (A.trace) {
       uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
       for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
-        const u96 v = ld96(S.acc + (e / m) * 3 * m, m, e % m);
+        const u96 v = from_offset_form(C, ld96(S.acc + (e / m) * 3 * m, m, e % m));
         tr[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); tr[2 * e + 1] = v.x2;
       }
     }
@@ -782,7 +809,7 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
       __syncthreads();
     }
     for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-      const u96 z = crt_lift<1, SH::LM>(C, zres + idx, (size_t)m);
+      const u96 z = crt_lift<1, SH::LM, 6 * LOGM + 8>(C, zres + idx, (size_t)m);
       out[((size_t)g * m + idx) * 2] = (uint64_t)z.x0 | ((uint64_t)z.x1 << 32); out[((size_t)g * m + idx) * 2 + 1] = z.x2;
     }
     __syncthreads();
@@ -796,7 +823,14 @@ __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_
   if (idx >= C.m) return;
   const u128 v = (u128)a[2 * idx] | ((u128)a[2 * idx + 1] << 64);
   int64_t d[2];
-  decompose(C, from128(v), Q96(C), draws ? draws[2 * idx] : 0, draws ? draws[2 * idx + 1] : 0, draws != nullptr, d[0], d[1]);
+  {
+    uint64_t dp0 = 0, dp1 = 0;
+    const u96 vo = to_offset_form(C, from128(v));
+#define SGFHE_FLATTEN_CASE(LOGM_) case LOGM_: if (draws) decompose_off_rand<3 * LOGM_ - 1>(C, vo, draws[2 * idx], draws[2 * idx + 1], dp0, dp1); else decompose_off<3 * LOGM_ - 1>(C, vo, dp0, dp1); break;
+    switch (C.logm) { SGFHE_FLATTEN_CASE(9) SGFHE_FLATTEN_CASE(10) SGFHE_FLATTEN_CASE(11) SGFHE_FLATTEN_CASE(12) default: SGFHE_FLATTEN_CASE(13) }
+#undef SGFHE_FLATTEN_CASE
+    d[0] = (int64_t)dp0 - ((int64_t)1 << 46); d[1] = (int64_t)dp1 - ((int64_t)1 << 46);
+  }
   for (int i = 0; i < 2; ++i) {
     const u128 r = d[i] >= 0 ? (u128)d[i] : C.Q - (u128)(-d[i]);
     out[((size_t)i * C.m + idx) * 2] = (uint64_t)r; out[((size_t)i * C.m + idx) * 2 + 1] = (uint64_t)(r >> 64);
@@ -828,11 +862,11 @@ __global__ void rns2_kernel(int op, size_t count, const uint64_t* __restrict__ a
 }
 
 // wide [2][m][2] -> accumulator scratch (SoA limbs) and back
-__global__ void acc_load_kernel(int m, const uint64_t* __restrict__ ab, uint32_t* acc) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void acc_load_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ ab, uint32_t* acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, m = C.m;
   if (e >= 2 * m) return;
   const u128 v = (u128)ab[2 * e] | ((u128)ab[2 * e + 1] << 64);
-  st96(acc + (e / m) * 3 * m, m, e % m, from128(v));
+  st96(acc + (e / m) * 3 * m, m, e % m, to_offset_form(C, from128(v)));
 }
 
 // =========================================================================================================
@@ -886,8 +920,14 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   dc->s = (uint64_t)s;
   dc->offs = h_mulmod(s, (1 + hp.B) % hp.Q, hp.Q);
   to_limbs(hp.Q, dc->Ql); to_limbs(dc->offs, dc->offl);
-  dc->barrett_mu = (uint64_t)(((u128)1 << (dc->sbits + 35)) / hp.Q);
-  dc->barrett_inv = ldexp((double)dc->barrett_mu, -64) * (1.0 - ldexp(1.0, -40));
+  if (dc->sbits != 6 * hp.logm + 8) return -1;                             // compile-time shift of barrett96
+  dc->barrett_inv = ldexp(1.0, dc->sbits - 16) / (double)hp.Q * (1.0 - ldexp(1.0, -40));
+  dc->inv35 = nextafter(nextafter(1.0 / 35.0, 1.0), 1.0);
+  dc->s46 = ((uint64_t)1 << 46) - dc->s;
+  {
+    const u128 K = ((u128)L << 30) + L + 1, KQ = K * hp.Q;                 // < 2^34 Q < 2^124
+    dc->KQ[0] = (uint32_t)KQ; dc->KQ[1] = (uint32_t)(KQ >> 32); dc->KQ[2] = (uint32_t)(KQ >> 64); dc->KQ[3] = (uint32_t)(KQ >> 96);
+  }
   const int NP = L > LM ? L : LM;
   for (int i = 0; i < NP; ++i) {
     const uint32_t p = primes[i];
@@ -1520,7 +1560,7 @@ extern "C" int sgfhe_external_product(sgfhe_ctx* c, const uint64_t* a, const uin
     if (e == cudaSuccess) e = cudaMemcpy(d_ab + 2 * (size_t)m, b, (size_t)m * 16, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, (size_t)4 * m * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-      acc_load_kernel<<<(2 * m + 255) / 256, 256>>>(m, d_ab, reinterpret_cast<uint32_t*>(c->d_scratch));
+      acc_load_kernel<<<(2 * m + 255) / 256, 256>>>(c->dc, d_ab, reinterpret_cast<uint32_t*>(c->d_scratch));
       ++g_launches;
       uint64_t* dummy = d_ab + 4 * (size_t)m;     // lwe pointers are not dereferenced for u when F_EXT is set ... but
       GateArgs A; memset(&A, 0, sizeof A);        // ... they are indexed for the pointer arithmetic only
