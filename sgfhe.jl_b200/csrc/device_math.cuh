@@ -68,6 +68,13 @@ __device__ __forceinline__ void gs_bfly(uint32_t& x, uint32_t& y, uint2 w, uint3
   x = min(s, s - p2);
   y = shoup_mul(d, w.x, w.y, p);
 }
+// The same with the NEGATED twiddle folded into the subtraction order: (x - y) (-w) = (y - x) w.  The v4 kernel reads the
+// mirrored FORWARD table entry w = -psi^-k directly and never forms the inverse twiddle.
+__device__ __forceinline__ void gs_bfly_negw(uint32_t& x, uint32_t& y, uint2 w, uint32_t p, uint32_t p2, uint32_t z) {
+  const uint32_t s = x + y + z, d = y - x + p2;
+  x = min(s, s - p2);
+  y = shoup_mul(d, w.x, w.y, p);
+}
 // Montgomery reduction of T < p 2^32 -> T 2^-32 mod p in [0,2p)
 __device__ __forceinline__ uint32_t redc(uint64_t T, uint32_t p, uint32_t pinv_neg) {
   const uint32_t mq = (uint32_t)T * pinv_neg;
@@ -87,7 +94,7 @@ __device__ __forceinline__ void fwd_block(uint32_t (&x)[1 << LOGR], const uint2*
       for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
   }
 }
-template <int LOGR>
+template <int LOGR, bool NEGW = false>
 __device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {
   constexpr int R = 1 << LOGR;
 #pragma unroll
@@ -96,7 +103,10 @@ __device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2*
 #pragma unroll
     for (int g = 0; g < (1 << l); ++g)
 #pragma unroll
-      for (int k = 0; k < half; ++k) gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
+      for (int k = 0; k < half; ++k) {
+        if (NEGW) gs_bfly_negw(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
+        else gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
+      }
   }
 }
 

@@ -89,20 +89,15 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
 //   EXT  (external-product seam): acc = z;   otherwise acc += x^u z - z  (mul_by_xj_minus_one, src/fhe.jl:554-556, applied
 //   to the product), evaluated on the unreduced CRT sums as V = acc + (KQ - S[j]) + (S[j-u] or KQ - S[j-u]) with ONE Barrett
 //   reduction; DEC: fused with the next step's gadget decomposition (RAND: with the caller's draws).
-template <int LOGM, int T, bool EXT, bool DEC, bool RAND>
+template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND>
 __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S, const uint4* sm4, int c,
-                                            const int64_t* __restrict__ draws_next, int u) {
+                                            const int64_t* __restrict__ draws_next, int u, u96 (&aq)[D]) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1, SB = 6 * LOGM + 8;
-  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
+  constexpr int NIT = m / T;
   const int tid = threadIdx.x;
   const uint4 KQ = make_uint4(C.KQ[0], C.KQ[1], C.KQ[2], C.KQ[3]);
   const uint4 OFF = make_uint4(C.offl[0], C.offl[1], C.offl[2], 0);
   uint32_t* acc = S.acc + c * 3 * m;
-  u96 aq[D];
-  if (!EXT) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) aq[d] = ld96(acc, m, tid + d * T);
-  }
 #pragma unroll 1
   for (int it0 = 0; it0 < NIT; it0 += D) {
 #pragma unroll
@@ -135,8 +130,10 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
 }
 
 // Phase C/D per accumulator polynomial: the UNREDUCED CRT sums S (four limbs each, device_math.cuh crt_sum) go to
-// shared memory, then update_poly.
-template <int LOGM, int T>
+// shared memory, then update_poly.  Every loop reads data written a whole step ago (largely evicted to HBM), so D
+// iterations of loads stay in flight and the first loads of each loop are issued one phase early, across the barriers.
+// OWN: each thread reads only residues it stored itself (v4 kernel), so those loads may precede the entry barrier.
+template <int LOGM, int T, bool OWN>
 __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
                                            const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
                                            unsigned long long* timing, long long& tprev) {
@@ -144,45 +141,56 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   uint4* sm4 = reinterpret_cast<uint4*>(sm);                 // [m] sums: 16 m bytes = the four transform buffers
-  // Both loops read data written a whole step ago (largely evicted to HBM): keep D iterations of loads in flight.
   constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
+  uint32_t yq[D][L];
+  u96 aq[D];
+  if (OWN) {
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int i = 0; i < L; ++i) yq[d][i] = S.zres[(size_t)i * 2 * m + tid + d * T];
+    __syncthreads();                                         // shared memory free for the CRT staging
+  }
   // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT sums run
   for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
   for (int c = 0; c < 2; ++c) {
-    {
-      const uint32_t* zr = S.zres + (size_t)c * m;
-      uint32_t yq[D][L];
+    const uint32_t* zr = S.zres + (size_t)c * m;
+    if (!OWN || c == 1) {
 #pragma unroll
       for (int d = 0; d < D; ++d)
 #pragma unroll
         for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + tid + d * T];
+    }
 #pragma unroll 1
-      for (int it0 = 0; it0 < NIT; it0 += D) {
+    for (int it0 = 0; it0 < NIT; it0 += D) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const int idx = tid + (it0 + d) * T;
-          uint32_t yc[L];
+      for (int d = 0; d < D; ++d) {
+        const int idx = tid + (it0 + d) * T;
+        uint32_t yc[L];
 #pragma unroll
-          for (int i = 0; i < L; ++i) yc[i] = yq[d][i];
-          if (it0 + d + D < NIT) {
+        for (int i = 0; i < L; ++i) yc[i] = yq[d][i];
+        if (it0 + d + D < NIT) {
 #pragma unroll
-            for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
-          }
-          sm4[idx] = crt_sum<0, L>(C, yc, 1);
+          for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
         }
+        sm4[idx] = crt_sum<0, L>(C, yc, 1);
       }
     }
     __syncthreads();
     SGFHE_TICK(5);
+    if (!ext) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) aq[d] = ld96(S.acc + c * 3 * m, m, tid + d * T);
+    }
     if (ext) {
-      if (!decompose_next) update_poly<LOGM, T, true, false, false>(C, S, sm4, c, nullptr, u);
-      else if (draws_next) update_poly<LOGM, T, true, true, true>(C, S, sm4, c, draws_next, u);
-      else update_poly<LOGM, T, true, true, false>(C, S, sm4, c, nullptr, u);
+      if (!decompose_next) update_poly<LOGM, T, D, true, false, false>(C, S, sm4, c, nullptr, u, aq);
+      else if (draws_next) update_poly<LOGM, T, D, true, true, true>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, true, true, false>(C, S, sm4, c, nullptr, u, aq);
     } else {
-      if (!decompose_next) update_poly<LOGM, T, false, false, false>(C, S, sm4, c, nullptr, u);
-      else if (draws_next) update_poly<LOGM, T, false, true, true>(C, S, sm4, c, draws_next, u);
-      else update_poly<LOGM, T, false, true, false>(C, S, sm4, c, nullptr, u);
+      if (!decompose_next) update_poly<LOGM, T, D, false, false, false>(C, S, sm4, c, nullptr, u, aq);
+      else if (draws_next) update_poly<LOGM, T, D, false, true, true>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, false, true, false>(C, S, sm4, c, nullptr, u, aq);
     }
     __syncthreads();
     SGFHE_TICK(6);
@@ -300,7 +308,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     __syncthreads();
     SGFHE_TICK(4);
   }
-  crt_update<LOGM, T>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
+  crt_update<LOGM, T, false>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
 
@@ -435,7 +443,8 @@ __device__ __forceinline__ void slice_sync() {
   if (Shape4<LOGM>::NB == 2) __syncwarp(); else group_bar64();
 }
 
-// twiddles of one radix-8 block from the staged forward table; inverse ones are mirrored and negated
+// twiddles of one radix-8 block from the staged forward table; the inverse passes take the MIRRORED forward entries
+// (psi^-bitrev(2^l+g) = -psi^bitrev(2^l+(g^(2^l-1)))) and fold the sign into the butterfly (gs_bfly_negw)
 template <bool FWD>
 __device__ __forceinline__ void block_twiddles(const uint2* tab, int lvl, int g, uint32_t p, uint2 (&w)[7]) {
   const int t1 = lvl + (FWD ? g : (g ^ (lvl - 1)));
@@ -443,13 +452,13 @@ __device__ __forceinline__ void block_twiddles(const uint2* tab, int lvl, int g,
   const uint4 a = *reinterpret_cast<const uint4*>(&tab[2 * t1]);
   const uint4 b0 = *reinterpret_cast<const uint4*>(&tab[4 * t1]);
   const uint4 b1 = *reinterpret_cast<const uint4*>(&tab[4 * t1 + 2]);
+  w[0] = w0;
   if (FWD) {
-    w[0] = w0; w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
+    w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
     w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w); w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
   } else {
-    w[0] = tw_neg(w0, p); w[1] = tw_neg(make_uint2(a.z, a.w), p); w[2] = tw_neg(make_uint2(a.x, a.y), p);
-    w[3] = tw_neg(make_uint2(b1.z, b1.w), p); w[4] = tw_neg(make_uint2(b1.x, b1.y), p);
-    w[5] = tw_neg(make_uint2(b0.z, b0.w), p); w[6] = tw_neg(make_uint2(b0.x, b0.y), p);
+    w[1] = make_uint2(a.z, a.w); w[2] = make_uint2(a.x, a.y);
+    w[3] = make_uint2(b1.z, b1.w); w[4] = make_uint2(b1.x, b1.y); w[5] = make_uint2(b0.z, b0.w); w[6] = make_uint2(b0.x, b0.y);
   }
 }
 
@@ -473,7 +482,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
       uint32_t x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = s[off[j]];
-      if (FWD) fwd_block<3>(x, w, p, p2, z); else inv_block<3>(x, w, p, p2, z);
+      if (FWD) fwd_block<3>(x, w, p, p2, z); else inv_block<3, true>(x, w, p, p2, z);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[off[j]] = x[j];
     }
@@ -581,8 +590,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
           const uint32_t kb[8] = {kk[2].x, kk[2].y, kk[2].z, kk[2].w, kk[3].x, kk[3].y, kk[3].z, kk[3].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            uint32_t d = x[e];
-            d = min(d, d - p2); d = min(d, d - p);
+            const uint32_t d = min(x[e], x[e] - p2);                 // [0, 2p): four products < 8 p^2 < 2^63
             sa[e] += (uint64_t)d * ka[e];
             sb[e] += (uint64_t)d * kb[e];
           }
@@ -591,9 +599,12 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
         block_twiddles<false>(tab, m / 8, blk, p, wi);
         uint32_t ya[8], yb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ya[e] = redc(sa[e], p, pinv); yb[e] = redc(sb[e], p, pinv); }
-        inv_block<3>(ya, wi, p, p2, z);
-        inv_block<3>(yb, wi, p, p2, z);
+        for (int e = 0; e < 8; ++e) {                                // redc of T < 8 p^2 lands in [0, 3p)
+          ya[e] = redc(sa[e], p, pinv); ya[e] = min(ya[e], ya[e] - p2);
+          yb[e] = redc(sb[e], p, pinv); yb[e] = min(yb[e], yb[e] - p2);
+        }
+        inv_block<3, true>(ya, wi, p, p2, z);
+        inv_block<3, true>(yb, wi, p, p2, z);
         *reinterpret_cast<uint4*>(sm + a0) = make_uint4(ya[0], ya[1], ya[2], ya[3]);
         *reinterpret_cast<uint4*>(sm + a1) = make_uint4(ya[4], ya[5], ya[6], ya[7]);
         *reinterpret_cast<uint4*>(sm + m + a0) = make_uint4(yb[0], yb[1], yb[2], yb[3]);
@@ -636,8 +647,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(4);
   }
-  __syncthreads();                                       // residues stored, shared memory free for the CRT staging
-  crt_update<LOGM, T>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
+  crt_update<LOGM, T, true>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
 #undef SGFHE_TICK
 }
 
