@@ -542,6 +542,13 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     __syncthreads();
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
+    {
+      // Top-stage twiddles of the NEXT prime into the other slot.  Its last readers (the previous prime's top inverse
+      // stages) are behind the barrier above; the barrier after the inverse passes publishes it to every warp before the
+      // next digit load reads it.  (Written after that barrier it would race with warps that run ahead of warp 0.)
+      const int nxt = (i + 1 == L) ? 0 : i + 1;
+      write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
+    }
     SGFHE_TICK(0);
     pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
     slice_sync<LOGM>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
@@ -620,7 +627,6 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     {
       const int nxt = (i + 1 == L) ? 0 : i + 1;          // TMA: next prime's forward table under the store phase
       if (tid == 0) stage_table(tab, tw_f + (size_t)nxt * m, m * 8, bar);
-      write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
     }
     if (i + 1 < L) {                                     // next prime's first digit words, requested under the store phase
 #pragma unroll

@@ -311,6 +311,19 @@ def test_full_gates_paper_size(so, sg):
     for g in range(G):
         y1, y2 = int(bits[g]), int(bits[G + g])
         assert tuple(so.decrypt_lwe(OP, sk, o[g]) for o in outs) == (y1 & y2, y1 | y2, y1 ^ y2)
+    # stress: eight waves of gates per SM, twice.  The persistent CTAs drift apart and every warp runs at its own pace;
+    # a missing barrier shows up as run-to-run differences (this caught a top-stage twiddle slot published without one).
+    W = 1184
+    reps = (2 * W + len(lwes) - 1) // len(lwes)
+    big, bb = np.concatenate([lwes] * reps)[: 2 * W], np.concatenate([bits] * reps)[: 2 * W]
+    o1 = sg.bootstrap_batch(bkey, None, big[:W], big[W:])
+    o2 = sg.bootstrap_batch(bkey, None, big[:W], big[W:])
+    skb = np.asarray(sk, dtype=bool)
+    y1, y2 = bb[:W].astype(np.int64), bb[W:].astype(np.int64)
+    for a, b, want in zip(o1, o2, (y1 & y2, y1 | y2, y1 ^ y2)):
+        assert np.array_equal(a, b)
+        b1 = (a[:, OP.n].astype(np.int64) - a[:, :OP.n][:, skb].astype(np.int64).sum(axis=1)) % OP.r
+        assert np.array_equal(((b1 + OP.Dr // 2) % OP.r) // OP.Dr, want)
     P.close()
 
 
