@@ -52,6 +52,16 @@ __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   return s;
 }
 static size_t scratch_bytes(int m) { return (size_t)56 * m; }
+
+// Position of transform-domain point idx inside a pre-transformed key polynomial.  At m = 8192 every lane of the fused
+// phase owns 16 consecutive points (64 bytes); the key is stored so that the four 16-byte loads of a warp are each
+// 512 contiguous bytes: point e = 16 lane + 4 t + r of a 512-point slice sits at 128 t + 4 lane + r.
+template <int LOGM>
+__host__ __device__ __forceinline__ int key_pos(int idx) {
+  if (LOGM != 13) return idx;
+  const int e = idx & 511;
+  return (idx & ~511) | (((e >> 2) & 3) << 7) | ((e >> 4) << 2) | (e & 3);
+}
 static size_t zres_bytes(int m, int L) { return (size_t)8 * L * m; }
 
 // accumulator init: a = 0, b = t(x) x^(-u_b) DQ   (src/fhe.jl:566-573, t(x) from src/fhe.jl:535-548)
@@ -263,13 +273,13 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
       constexpr int NIT = m / T;
       uint32_t kq[3][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { kq[0][q] = __ldg(&K[q * m + tid]); if (NIT > 1) kq[1][q] = __ldg(&K[q * m + tid + T]); }
+      for (int q = 0; q < 8; ++q) { kq[0][q] = __ldg(&K[q * m + key_pos<LOGM>(tid)]); if (NIT > 1) kq[1][q] = __ldg(&K[q * m + key_pos<LOGM>(tid + T)]); }
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         const int idx = tid + it * T;
         if (it + 2 < NIT) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) kq[(it + 2) % 3][q] = __ldg(&K[q * m + idx + 2 * T]);
+          for (int q = 0; q < 8; ++q) kq[(it + 2) % 3][q] = __ldg(&K[q * m + key_pos<LOGM>(idx + 2 * T)]);
         }
         uint64_t sa = 0, sb = 0;
         const int si = swz(idx);
@@ -430,13 +440,14 @@ __device__ __forceinline__ void group_bar64() {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");
 }
 // With two radix-8 blocks per thread and polynomial (m = 8192) each WARP owns one 512-element slice outright (blocks
-// lane and lane + 32 of slice warp_id), so the three shared-memory passes and the fused phase between the top stages
-// exchange data inside a warp only: __syncwarp replaces the block-level barriers and the 16 warps drift freely
-// (tools/microbench/bfly2.cu: a barrier per pass costs 19-45 % of the butterfly throughput).
+// 2 lane and 2 lane + 1 of slice warp_id), so the three shared-memory passes and the fused phase between the top stages
+// exchange data inside a warp only: __syncwarp replaces the block-level barriers and the 16 warps drift freely.
+// The two blocks of a thread are ADJACENT: in the strided passes they share their twiddles and their elements are
+// neighbours in memory, so every access is 64 bits wide (half the LDS/STS instructions; swz keeps bit 0).
 template <int LOGM>
 __device__ __forceinline__ int block_of(int tid, int q) {
   using S4 = Shape4<LOGM>;
-  return S4::NB == 2 ? (((tid >> 5) << 6) | (q << 5) | (tid & 31)) : tid + q * S4::T;
+  return S4::NB == 2 ? (((tid >> 5) << 6) | ((tid & 31) << 1) | q) : tid + q * S4::T;
 }
 template <int LOGM>
 __device__ __forceinline__ void slice_sync() {
@@ -467,6 +478,28 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   using S4 = Shape4<LOGM>;
   constexpr int M = S4::M;
   const uint32_t p2 = 2 * p;
+  if constexpr (S4::NB == 2 && B >= 1) {
+    // blocks blk and blk + 1 (blk even): same twiddles, elements (e, e + 1) adjacent and 8-byte aligned
+    const int blk = block_of<LOGM>(threadIdx.x, 0);
+    const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
+    uint2 w[7];
+    block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = swz(base + (j << B));
+#pragma unroll
+    for (int poly = 0; poly < NPOLY; ++poly) {
+      uint32_t* s = sm + poly * M;
+      uint32_t x[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const uint2 v = *reinterpret_cast<const uint2*>(s + off[j]); x[j] = v.x; y[j] = v.y; }
+      if (FWD) { fwd_block<3>(x, w, p, p2, z); fwd_block<3>(y, w, p, p2, z); }
+      else { inv_block<3, true>(x, w, p, p2, z); inv_block<3, true>(y, w, p, p2, z); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint2*>(s + off[j]) = make_uint2(x[j], y[j]);
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < S4::NB; ++q) {
     const int blk = block_of<LOGM>(threadIdx.x, q);
@@ -555,10 +588,9 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
     {                                                    // the first set is requested before the stride-8 pass
-      const uint4* k0 = reinterpret_cast<const uint4*>(K + 8 * block_of<LOGM>(tid, 0));
-      kq[0][0] = __ldg(k0); kq[0][1] = __ldg(k0 + 1);
-      const uint4* k1 = reinterpret_cast<const uint4*>(K + m + 8 * block_of<LOGM>(tid, 0));
-      kq[0][2] = __ldg(k1); kq[0][3] = __ldg(k1 + 1);
+      const int kb = key_pos<LOGM>(8 * block_of<LOGM>(tid, 0)), kh = key_pos<LOGM>(8 * block_of<LOGM>(tid, 0) + 4);
+      kq[0][0] = __ldg(reinterpret_cast<const uint4*>(K + kb)); kq[0][1] = __ldg(reinterpret_cast<const uint4*>(K + kh));
+      kq[0][2] = __ldg(reinterpret_cast<const uint4*>(K + m + kb)); kq[0][3] = __ldg(reinterpret_cast<const uint4*>(K + m + kh));
     }
     pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
     __syncwarp();                                        // bits [0,6) stay inside groups of 8 consecutive threads
@@ -580,10 +612,11 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
           const int sidx = q * 4 + j;
           if (sidx + 1 < NB * 4) {                       // prefetch the next (block, poly) key words
             const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
-            const uint4* k0 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj) * m + 8 * block_of<LOGM>(tid, nq));
-            const uint4* k1 = reinterpret_cast<const uint4*>(K + (size_t)(2 * nj + 1) * m + 8 * block_of<LOGM>(tid, nq));
-            kq[(sidx + 1) & 1][0] = __ldg(k0); kq[(sidx + 1) & 1][1] = __ldg(k0 + 1);
-            kq[(sidx + 1) & 1][2] = __ldg(k1); kq[(sidx + 1) & 1][3] = __ldg(k1 + 1);
+            const int kb = key_pos<LOGM>(8 * block_of<LOGM>(tid, nq)), kh = key_pos<LOGM>(8 * block_of<LOGM>(tid, nq) + 4);
+            const uint32_t* r0 = K + (size_t)(2 * nj) * m;
+            const uint32_t* r1 = K + (size_t)(2 * nj + 1) * m;
+            kq[(sidx + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(r0 + kb)); kq[(sidx + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(r0 + kh));
+            kq[(sidx + 1) & 1][2] = __ldg(reinterpret_cast<const uint4*>(r1 + kb)); kq[(sidx + 1) & 1][3] = __ldg(reinterpret_cast<const uint4*>(r1 + kh));
           }
           uint32_t x[8];
           {
@@ -760,7 +793,7 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     uint32_t v = sm[swz(idx)];
     v = min(v, v - p2); v = min(v, v - p);
-    dst[idx] = csub(shoup_mul(v, C.mont[i], C.mont_sh[i], p), p);
+    dst[key_pos<LOGM>(idx)] = csub(shoup_mul(v, C.mont[i], C.mont_sh[i], p), p);
   }
 }
 
@@ -1236,7 +1269,7 @@ extern "C" int sgfhe_bkey_export(sgfhe_ctx* c, int32_t rows, void* blob, uint64_
   if (!blob || bytes < need) return fail(SGFHE_ERR_ARG, "blob buffer too small");
   CK(cudaSetDevice(c->device));
   KeyBlobHeader h; memset(&h, 0, sizeof h);
-  h.magic = KEY_MAGIC; h.version = 1; h.n = c->hp.n; h.m = c->hp.m; h.L = c->dc.L; h.rows = rows;
+  h.magic = KEY_MAGIC; h.version = 2; h.n = c->hp.n; h.m = c->hp.m; h.L = c->dc.L; h.rows = rows;
   for (int i = 0; i < MAXP; ++i) h.p[i] = c->dc.p[i];
   h.Q[0] = (uint64_t)c->hp.Q; h.Q[1] = (uint64_t)(c->hp.Q >> 64);
   memcpy(blob, &h, sizeof h);
@@ -1247,7 +1280,7 @@ extern "C" int sgfhe_bkey_export(sgfhe_ctx* c, int32_t rows, void* blob, uint64_
 extern "C" int sgfhe_bkey_import(sgfhe_ctx* c, const void* blob, uint64_t bytes) {
   if (!c || !blob || bytes < sizeof(KeyBlobHeader)) return fail(SGFHE_ERR_ARG, "bad blob");
   KeyBlobHeader h; memcpy(&h, blob, sizeof h);
-  if (h.magic != KEY_MAGIC || h.version != 1) return fail(SGFHE_ERR_ARG, "not a serialised sgfhe key");
+  if (h.magic != KEY_MAGIC || h.version != 2) return fail(SGFHE_ERR_ARG, "not a serialised sgfhe key");
   if (h.n != c->hp.n || h.m != c->hp.m || h.L != c->dc.L || h.Q[0] != (uint64_t)c->hp.Q || h.Q[1] != (uint64_t)(c->hp.Q >> 64))
     return fail(SGFHE_ERR_ARG, "serialised key belongs to other parameters");
   for (int i = 0; i < h.L; ++i) if (h.p[i] != c->dc.p[i]) return fail(SGFHE_ERR_ARG, "serialised key uses another RNS basis");
