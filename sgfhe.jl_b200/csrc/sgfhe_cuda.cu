@@ -709,6 +709,10 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
   __syncthreads();
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
+  if (A.stagger_cycles > 0) {                            // experiment knob: CTA b starts (b % slots) * cycles late
+    const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
+    while (clock64() - t0 < wait) __nanosleep(256);
+  }
   for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
