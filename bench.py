@@ -439,4 +439,14 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner when the
+    # environment sets NCCL_DEBUG), so everything except that line is sent to stderr: fd 1 points at stderr while the
+    # benchmark runs and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
+    try:
+        main()
+    finally:
+        _real_stdout.flush()

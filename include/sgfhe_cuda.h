@@ -143,6 +143,23 @@ int sgfhe_rns2_op_device(int32_t device, int32_t op, uint64_t count, const uint6
                          const uint64_t* d_b1, const uint64_t* d_b2, uint64_t M1, uint64_t M2, uint64_t* d_o1,
                          uint64_t* d_o2, void* stream);
 
+/* split_ciphertext (src/fhe.jl:287-290) on the device: `count` RLWE ciphertexts over Z_r, polynomials of length N
+ * (N = n for a PackedCiphertext, N = m for a Ciphertext), a and b as [count][N] uint64 -> count * n LWEs [count*n][n+1]:
+ * LWE i = (extract(a, i, n), b[i]) with extract as in src/fhe.jl:237-244 (reversed window, negated wrap-around).
+ * Device buffers, asynchronous on `stream`; outputs feed sgfhe_bootstrap_batch_device directly. */
+int sgfhe_split_ciphertext_device(sgfhe_ctx* ctx, int32_t count, int32_t N, const uint64_t* d_a, const uint64_t* d_b,
+                                  uint64_t* d_lwes, void* stream);
+/* same with host buffers */
+int sgfhe_split_ciphertext(sgfhe_ctx* ctx, int32_t count, int32_t N, const uint64_t* a, const uint64_t* b, uint64_t* lwes);
+
+/* decrypt(key, ::EncryptedBit) (src/fhe.jl:504-507) for a batch: lwes [count][n+1] over Z_r, sk n bytes (0/1);
+ * out[i] = ((b - <a, s>) + Dr/2 mod r) / Dr as one byte (0 or 1; larger values are the reference's InexactError and
+ * are returned as they are for the caller to reject).  Device buffers, asynchronous on `stream`. */
+int sgfhe_decrypt_bits_device(sgfhe_ctx* ctx, int32_t count, const uint64_t* d_lwes, const uint8_t* d_sk, uint8_t* d_out,
+                              void* stream);
+/* same with host buffers */
+int sgfhe_decrypt_bits(sgfhe_ctx* ctx, int32_t count, const uint64_t* lwes, const uint8_t* sk, uint8_t* out);
+
 /* Kernel launches issued by this library in the calling process since load (for bench accounting). */
 uint64_t sgfhe_launch_count(void);
 

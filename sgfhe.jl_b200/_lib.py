@@ -22,6 +22,7 @@ SYMBOLS = [
     "sgfhe_bootstrap_internal_batch", "sgfhe_shortened_products",
     "sgfhe_scheme2_params_derive", "sgfhe_rns2_op", "sgfhe_rns2_op_device",
     "sgfhe_bkey_export_size", "sgfhe_bkey_export", "sgfhe_bkey_import",
+    "sgfhe_split_ciphertext", "sgfhe_split_ciphertext_device", "sgfhe_decrypt_bits", "sgfhe_decrypt_bits_device",
 ]
 
 
@@ -71,6 +72,10 @@ def lib():
         L.sgfhe_bkey_export_size.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
         L.sgfhe_bkey_export.argtypes = [vp, i32, vp, C.c_uint64]
         L.sgfhe_bkey_import.argtypes = [vp, vp, C.c_uint64]
+        L.sgfhe_split_ciphertext.argtypes = [vp, i32, i32, u64p, u64p, u64p]
+        L.sgfhe_split_ciphertext_device.argtypes = [vp, i32, i32, u64p, u64p, u64p, vp]
+        L.sgfhe_decrypt_bits.argtypes = [vp, i32, u64p, vp, vp]
+        L.sgfhe_decrypt_bits_device.argtypes = [vp, i32, u64p, vp, vp, vp]
         L.sgfhe_scheme2_params_derive.argtypes = [i32, C.POINTER(Scheme2ParamsC)]
         L.sgfhe_rns2_op.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p]
         L.sgfhe_rns2_op_device.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, vp]

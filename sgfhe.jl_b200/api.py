@@ -149,6 +149,31 @@ def split_ciphertext(ct) -> list[EncryptedBit]:
     return [EncryptedBit(LWE(_extract_r(ct.a, i, P.n, P.r), ct.b[i - 1])) for i in range(1, P.n + 1)]
 
 
+def split_ciphertexts(cts) -> np.ndarray:
+    """split_ciphertext (src/fhe.jl:287-290) for a list of ciphertexts on the GPU: uint64[len(cts) * n, n + 1], LWE rows in
+    the reference's order, ready for `bootstrap_batch`."""
+    P = cts[0].params
+    a = np.ascontiguousarray(np.stack([c.a for c in cts]), np.uint64)
+    b = np.ascontiguousarray(np.stack([c.b for c in cts]), np.uint64)
+    out = np.zeros((len(cts) * P.n, P.n + 1), np.uint64)
+    check(_lib.lib().sgfhe_split_ciphertext(P.ctx, len(cts), a.shape[1], _ptr(a), _ptr(b), _ptr(out)))
+    return out
+
+
+def decrypt_bits(key: PrivateKey, lwes: np.ndarray) -> np.ndarray:
+    """decrypt(key, ::EncryptedBit) (src/fhe.jl:504-507) for an array of LWEs uint64[count, n + 1] on the GPU -> bool[count]."""
+    P = key.params
+    lwes = np.ascontiguousarray(lwes, np.uint64)
+    if lwes.ndim != 2 or lwes.shape[1] != P.n + 1:
+        raise SgfheError("LWE array must be [count, n+1]")
+    sk = np.ascontiguousarray(key.key, np.uint8)
+    out = np.zeros(lwes.shape[0], np.uint8)
+    check(_lib.lib().sgfhe_decrypt_bits(P.ctx, lwes.shape[0], _ptr(lwes), _ptr(sk), _ptr(out)))
+    if (out > 1).any():
+        raise SgfheError("InexactError: decrypted value is not a Bool (src/fhe.jl:506)")
+    return out.astype(bool)
+
+
 def decrypt(key: PrivateKey, ct):
     """decrypt(key, ::EncryptedBit) src/fhe.jl:504-507; decrypt(key, ::PackedCiphertext) src/fhe.jl:471-494."""
     P = key.params

@@ -498,8 +498,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint2*>(s + off[j]) = make_uint2(x[j], y[j]);
     }
-    return;
-  }
+  } else {
 #pragma unroll
   for (int q = 0; q < S4::NB; ++q) {
     const int blk = block_of<LOGM>(threadIdx.x, q);
@@ -519,6 +518,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[off[j]] = x[j];
     }
+  }
   }
 }
 
@@ -912,6 +912,34 @@ __global__ void rns2_kernel(int op, size_t count, const uint64_t* __restrict__ a
     else { r1 = x1 >= y1 ? x1 - y1 : x1 + M1 - y1; r2 = x2 >= y2 ? x2 - y2 : x2 + M2 - y2; }              // rns.jl:59-60
     o1[i] = r1; o2[i] = r2;
   }
+}
+
+// split_ciphertext (src/fhe.jl:287-290): one CTA row per output LWE; i = blockIdx.x % n + 1 is the reference's 1-based index.
+// extract(a, i, n) (src/fhe.jl:237-244): element k (1-based) is a[i-k+1] while k <= i, else -a[N+i+1-k].
+__global__ void split_kernel(int n, int N, uint64_t r, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                             uint64_t* __restrict__ lwes) {
+  const int ct = blockIdx.x / n, i = blockIdx.x % n + 1;
+  const uint64_t* ap = a + (size_t)ct * N;
+  uint64_t* out = lwes + (size_t)blockIdx.x * (n + 1);
+  for (int k = threadIdx.x + 1; k <= n; k += blockDim.x) {
+    uint64_t v;
+    if (k <= i) v = ap[i - k];                                   // a.coeffs[i-k+1]
+    else { const uint64_t t = ap[N + i - k]; v = t ? r - t : 0; }     // -a.coeffs[N+i+1-k]
+    out[k - 1] = v;
+  }
+  if (threadIdx.x == 0) out[n] = b[(size_t)ct * N + i - 1];
+}
+
+// decrypt(key, ::EncryptedBit) (src/fhe.jl:504-507): one warp per LWE
+__global__ void decrypt_kernel(int n, int count, uint64_t rmask, uint64_t Dr, const uint64_t* __restrict__ lwes,
+                               const uint8_t* __restrict__ sk, uint8_t* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const uint64_t* l = lwes + (size_t)w * (n + 1);
+  uint64_t acc = 0;
+  for (int k = lane; k < n; k += 32) acc += sk[k] ? l[k] : 0;
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[w] = (uint8_t)((((l[n] - acc) + Dr / 2) & rmask) / Dr);
 }
 
 // wide [2][m][2] -> accumulator scratch (SoA limbs) and back
@@ -1475,6 +1503,71 @@ extern "C" int sgfhe_bootstrap_trace(sgfhe_ctx* c, const uint64_t* lwe1, const u
   return SGFHE_OK;
 }
 
+
+extern "C" int sgfhe_split_ciphertext_device(sgfhe_ctx* c, int32_t count, int32_t N, const uint64_t* d_a, const uint64_t* d_b,
+                                             uint64_t* d_lwes, void* stream) {
+  if (!c || !d_a || !d_b || !d_lwes) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count < 0) return fail(SGFHE_ERR_ARG, "negative count");
+  if (N < c->hp.n) return fail(SGFHE_ERR_ARG, "polynomial shorter than n (src/fhe.jl:238)");
+  if (count == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  split_kernel<<<(unsigned)count * c->hp.n, 256, 0, (cudaStream_t)stream>>>(c->hp.n, N, c->hp.r, d_a, d_b, d_lwes);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_split_ciphertext(sgfhe_ctx* c, int32_t count, int32_t N, const uint64_t* a, const uint64_t* b, uint64_t* lwes) {
+  if (!c || !a || !b || !lwes) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count < 0) return fail(SGFHE_ERR_ARG, "negative count");
+  if (N < c->hp.n) return fail(SGFHE_ERR_ARG, "polynomial shorter than n (src/fhe.jl:238)");
+  if (count == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t in_w = (size_t)count * N, out_w = (size_t)count * c->hp.n * (c->hp.n + 1);
+  uint64_t* d = nullptr;
+  if (cudaMalloc(&d, (2 * in_w + out_w) * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  cudaError_t e = cudaMemcpy(d, a, in_w * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + in_w, b, in_w * 8, cudaMemcpyHostToDevice);
+  int rc = SGFHE_OK;
+  if (e == cudaSuccess) rc = sgfhe_split_ciphertext_device(c, count, N, d, d + in_w, d + 2 * in_w, nullptr);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(lwes, d + 2 * in_w, out_w * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("split_ciphertext: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_decrypt_bits_device(sgfhe_ctx* c, int32_t count, const uint64_t* d_lwes, const uint8_t* d_sk, uint8_t* d_out,
+                                         void* stream) {
+  if (!c || !d_lwes || !d_sk || !d_out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count < 0) return fail(SGFHE_ERR_ARG, "negative count");
+  if (count == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const int threads = 256, blocks = (int)(((size_t)count * 32 + threads - 1) / threads);
+  decrypt_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(c->hp.n, count, c->hp.r - 1, c->hp.Dr, d_lwes, d_sk, d_out);
+  ++g_launches;
+  CK(cudaGetLastError());
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_decrypt_bits(sgfhe_ctx* c, int32_t count, const uint64_t* lwes, const uint8_t* sk, uint8_t* out) {
+  if (!c || !lwes || !sk || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (count < 0) return fail(SGFHE_ERR_ARG, "negative count");
+  if (count == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t lw = (size_t)count * (c->hp.n + 1) * 8;
+  uint8_t* d = nullptr;
+  if (cudaMalloc(&d, lw + c->hp.n + count) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  cudaError_t e = cudaMemcpy(d, lwes, lw, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + lw, sk, c->hp.n, cudaMemcpyHostToDevice);
+  int rc = SGFHE_OK;
+  if (e == cudaSuccess) rc = sgfhe_decrypt_bits_device(c, count, reinterpret_cast<uint64_t*>(d), d + lw, d + lw + c->hp.n, nullptr);
+  if (!rc && e == cudaSuccess) e = cudaMemcpy(out, d + lw + c->hp.n, count, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("decrypt_bits: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
 
 static uint64_t h_isqrt(uint64_t x) { uint64_t r = 0; while ((r + 1) * (r + 1) <= x) ++r; return r; }
 

@@ -327,6 +327,29 @@ def test_full_gates_paper_size(so, sg):
     P.close()
 
 
+def test_split_and_decrypt_on_device(env64, sg):
+    """SURVEY 8(f) row 4: split_ciphertext / extract (src/fhe.jl:237-244, 287-290) and decrypt(::EncryptedBit)
+    (src/fhe.jl:504-507) on the GPU equal the host mirror, for packed ciphertexts (N = n) and for the length-m ciphertext
+    of pack_encrypted_bits (N = m, wrap-around taken from the tail of the long polynomial)."""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    rng = np.random.default_rng(11)
+    skey = sg.PrivateKey(P, rng)
+    msgs = [rng.integers(0, 2, size=P.n, dtype=np.uint8) for _ in range(3)]
+    cts = [sg.encrypt(skey, rng, m_) for m_ in msgs]
+    got = sg.split_ciphertexts(cts)
+    want = np.stack([e.lwe.flat() for c in cts for e in sg.split_ciphertext(c)])
+    assert np.array_equal(got, want)
+    dec = sg.decrypt_bits(skey, got)
+    assert np.array_equal(dec, np.concatenate(msgs).astype(bool))
+    assert [bool(x) for x in dec[:8]] == [sg.decrypt(skey, sg.EncryptedBit(sg.LWE(r_[:-1], r_[-1]))) for r_ in got[:8]]
+    long_ct = sg.Ciphertext(P, rng.integers(0, P.r, size=P.m, dtype=np.uint64), rng.integers(0, P.r, size=P.m, dtype=np.uint64))
+    got2 = sg.split_ciphertexts([long_ct])
+    want2 = np.stack([e.lwe.flat() for e in sg.split_ciphertext(long_ct)])
+    assert np.array_equal(got2, want2)
+    with pytest.raises(sg.SgfheError):
+        sg.decrypt_bits(skey, got[:, :-1])
+
+
 def test_transformed_key_roundtrip(env64, sg, tmp_path):
     """serialise the pre-transformed key, load it into a fresh context, same ciphertexts out; wrong parameters rejected"""
     P, OP, sk, key, bits, lwes, bkey = env64
