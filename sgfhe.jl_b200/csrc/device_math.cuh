@@ -33,7 +33,8 @@ struct DevConst {
   uint32_t p[MAXP], pinv_neg[MAXP], dig_mu[MAXP], vinv[MAXP], vk[MAXP];
   uint32_t r32[MAXP], r64[MAXP];            // 2^32 mod p, 2^64 mod p
   uint32_t qmodp[MAXP];                     // Q mod p
-  uint64_t mu64[MAXP];                      // floor(2^64 / p)
+  uint32_t r32_sh[MAXP], r64_sh[MAXP];      // their Shoup companions
+  uint64_t Qhalf[2];                        // floor(Q / 2) as (lo, hi)
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
   uint32_t dig_negc[MAXP];                  // p - (2^46 mod p)
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
@@ -341,16 +342,19 @@ __device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t
   return lo - __umulhi(hi, mu) * p + negc;
 }
 
-// canonical value of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p)
-__device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, u128 c) {
-  const uint32_t p = C.p[i];
-  // c = c2 2^64 + c1 2^32 + c0  ->  t = c2 (2^64 mod p) + c1 (2^32 mod p) + c0 < 2^63, then Barrett with mu = floor(2^64 / p)
-  const uint64_t t = (uint64_t)(uint32_t)(c >> 64) * C.r64[i] + (uint64_t)(uint32_t)(c >> 32) * C.r32[i] + (uint32_t)c;
-  const uint64_t q = __umul64hi(t, C.mu64[i]);                      // in [t/p - 1, t/p]
-  uint32_t r = (uint32_t)(t - q * p);                               // in [0, 2p)
-  r = csub(r, p);
-  if (c > (C.Q >> 1)) r = r >= C.qmodp[i] ? r - C.qmodp[i] : r + p - C.qmodp[i];
-  return r;
+// canonical value c = lo + 2^64 hi of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p).
+// c = w0 + w1 2^32 + w2 2^64 with 32-bit words: two Shoup products by (2^32 mod p), (2^64 mod p), and w0 reduced by its
+// top two bits (p > 2^30 - 2^27, checked on the host, keeps w0 - (w0 >> 30) p below 2p).
+__device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, uint64_t lo, uint64_t hi) {
+  const uint32_t p = C.p[i], p2 = 2 * p;
+  const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi;
+  uint32_t t = shoup_mul(w1, C.r32[i], C.r32_sh[i], p) + shoup_mul(w2, C.r64[i], C.r64_sh[i], p);   // [0, 4p)
+  t = min(t, t - p2);
+  t += w0 - (w0 >> 30) * p;                                                                          // [0, 4p)
+  t = min(t, t - p2); t = min(t, t - p);
+  const bool upper = hi > C.Qhalf[1] || (hi == C.Qhalf[1] && lo > C.Qhalf[0]);                      // c > Q/2: c - Q
+  const uint32_t tn = t - C.qmodp[i];
+  return upper ? min(tn, tn + p) : t;
 }
 
 // 128-bit limb helpers for the unreduced CRT sums

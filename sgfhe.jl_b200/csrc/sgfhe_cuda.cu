@@ -783,7 +783,7 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int e = idx + k * STR;
-      x[k] = centred_mod(C, i, (u128)src[2 * e] | ((u128)src[2 * e + 1] << 64));
+      x[k] = centred_mod(C, i, src[2 * e], src[2 * e + 1]);
     }
     fwd_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
@@ -824,18 +824,30 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
       if (threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_f + (size_t)i * m, wt);
-      for (int e = threadIdx.x; e < 2 * STR; e += blockDim.x) {
-        const int c = e / STR, idx = e % STR;
-        const uint64_t* src = (c ? b : a) + (size_t)g * m * 2;
-        uint32_t x[R];
+      {
+        // operand coefficients (16 bytes each) one iteration ahead of their reduction
+        constexpr int NITER = 2 * STR / SH::T;
+        ulonglong2 cur[R], nxt[R];
+        auto fetch = [&](ulonglong2 (&dst)[R], int e) {
+          const int c = e / STR, idx = e % STR;
+          const ulonglong2* src = reinterpret_cast<const ulonglong2*>((c ? b : a) + (size_t)g * m * 2);
 #pragma unroll
-        for (int k = 0; k < R; ++k) {
-          const int q = idx + k * STR;
-          x[k] = centred_mod(C, i, (u128)src[2 * q] | ((u128)src[2 * q + 1] << 64));
+          for (int k = 0; k < R; ++k) dst[k] = src[idx + k * STR];
+        };
+        fetch(cur, threadIdx.x);
+#pragma unroll
+        for (int it = 0; it < NITER; ++it) {
+          const int e = threadIdx.x + it * SH::T, c = e / STR, idx = e % STR;
+          if (it + 1 < NITER) fetch(nxt, e + SH::T);
+          uint32_t x[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) x[k] = centred_mod(C, i, cur[k].x, cur[k].y);
+          fwd_block<REM>(x, wt, p, p2, C.zero);
+#pragma unroll
+          for (int k = 0; k < R; ++k) sm[c * m + swz(idx + k * STR)] = x[k];
+#pragma unroll
+          for (int k = 0; k < R; ++k) cur[k] = nxt[k];
         }
-        fwd_block<REM>(x, wt, p, p2, C.zero);
-#pragma unroll
-        for (int k = 0; k < R; ++k) sm[c * m + swz(idx + k * STR)] = x[k];
       }
       __syncthreads();
       mbar_wait(bar, parity); parity ^= 1;
@@ -997,6 +1009,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   dc->n = hp.n; dc->m = hp.m; dc->logm = hp.logm; dc->logr = hp.logr; dc->kB = hp.kB; dc->L = L; dc->LM = LM;
   dc->sbits = h_bits(hp.Q) - 1;
   dc->Q = hp.Q; dc->DQ = hp.DQ; dc->B = hp.B;
+  dc->Qhalf[0] = (uint64_t)(hp.Q >> 1); dc->Qhalf[1] = (uint64_t)(hp.Q >> 65);
   const u128 s = hp.B / 2 - 1;                       // B is even (src/utils.jl:162-166)
   dc->s = (uint64_t)s;
   dc->offs = h_mulmod(s, (1 + hp.B) % hp.Q, hp.Q);
@@ -1021,7 +1034,9 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     dc->r32[i] = (uint32_t)(((uint64_t)1 << 32) % p);
     dc->r64[i] = (uint32_t)((((u128)1) << 64) % p);
     dc->qmodp[i] = (uint32_t)(hp.Q % p);
-    dc->mu64[i] = (uint64_t)((((u128)1) << 64) / p);
+    dc->r32_sh[i] = (uint32_t)(((uint64_t)dc->r32[i] << 32) / p);
+    dc->r64_sh[i] = (uint32_t)(((uint64_t)dc->r64[i] << 32) / p);
+    if (5ull * ((1u << 30) - p) >= (1u << 30)) return -1;                  // centred_mod's reduction of the low word
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
     dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p);
