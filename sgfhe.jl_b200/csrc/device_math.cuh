@@ -144,6 +144,14 @@ __device__ __forceinline__ void stage_table(void* dst, const void* src, uint32_t
     bulk_g2s(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o < CH ? bytes - o : CH, bar);
 }
 
+// Ampere-style asynchronous 4-byte copies global -> shared (SASS LDGSTS): no destination registers, so data can be
+// requested across a barrier without lengthening any register live range
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // inverse block without its last level (l = 0, pairs (k, k + R/2)): the caller folds a scaling into that level
 template <int LOGR>
 __device__ __forceinline__ void inv_block_upper(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {

@@ -187,11 +187,25 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
         sm4[idx] = crt_sum<0, L>(C, yc, 1);
       }
     }
+    constexpr int DS = OWN ? D : 0;                          // accumulator words of the first DS iterations: async copies
+    uint32_t* stg = sm + 4 * m;                              // [DS][3][T] in the (idle) twiddle-table region of the v4 kernel
+    if (!ext && DS) {
+#pragma unroll
+      for (int d = 0; d < DS; ++d)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) cp_async4(stg + (d * 3 + l) * T + tid, S.acc + (c * 3 + l) * m + tid + d * T);
+      cp_async_commit();
+    }
     __syncthreads();
     SGFHE_TICK(5);
     if (!ext) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) aq[d] = ld96(S.acc + c * 3 * m, m, tid + d * T);
+      for (int d = DS; d < D; ++d) aq[d] = ld96(S.acc + c * 3 * m, m, tid + d * T);
+      if (DS) {
+        cp_async_wait_all();
+#pragma unroll
+        for (int d = 0; d < DS; ++d) { aq[d].x0 = stg[(d * 3) * T + tid]; aq[d].x1 = stg[(d * 3 + 1) * T + tid]; aq[d].x2 = stg[(d * 3 + 2) * T + tid]; }
+      }
     }
     if (ext) {
       if (!decompose_next) update_poly<LOGM, T, D, true, false, false>(C, S, sm4, c, nullptr, u, aq);
@@ -658,8 +672,9 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
     __syncthreads();                                     // last reader of `tab` for this prime is done
     {
-      const int nxt = (i + 1 == L) ? 0 : i + 1;          // TMA: next prime's forward table under the store phase
-      if (tid == 0) stage_table(tab, tw_f + (size_t)nxt * m, m * 8, bar);
+      // TMA: next prime's forward table under the store phase.  After the last prime the table region serves the
+      // CRT/update phases as a staging area; prime 0's table for the next step is requested after them.
+      if (tid == 0 && i + 1 < L) stage_table(tab, tw_f + (size_t)(i + 1) * m, m * 8, bar);
     }
     if (i + 1 < L) {                                     // next prime's first digit words, requested under the store phase
 #pragma unroll
@@ -687,6 +702,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     SGFHE_TICK(4);
   }
   crt_update<LOGM, T, true>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
+  if (tid == 0) stage_table(tab, tw_f, m * 8, bar);      // ends with a barrier: the staging area is free again
 #undef SGFHE_TICK
 }
 
