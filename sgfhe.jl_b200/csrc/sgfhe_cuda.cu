@@ -161,12 +161,29 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
       for (int i = 0; i < L; ++i) yq[d][i] = S.zres[(size_t)i * 2 * m + tid + d * T];
     __syncthreads();                                         // shared memory free for the CRT staging
   }
+  // first residues of the SECOND polynomial: async copies into the idle twiddle-table region (behind the accumulator
+  // staging), requested now, consumed when the second CRT loop starts
+  constexpr bool RS = OWN && (size_t)D * (3 + L) * T * 4 <= (size_t)m * 8;
+  uint32_t* stg_res = sm + 4 * m + D * 3 * T;                // [D][L][T]
+  if (RS) {
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int i = 0; i < L; ++i) cp_async4(stg_res + (d * L + i) * T + tid, S.zres + (size_t)m + (size_t)i * 2 * m + tid + d * T);
+    cp_async_commit();
+  }
   // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT sums run
   for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
   for (int c = 0; c < 2; ++c) {
     const uint32_t* zr = S.zres + (size_t)c * m;
-    if (!OWN || c == 1) {
+    if (RS && c == 1) {
+      cp_async_wait_all();
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int i = 0; i < L; ++i) yq[d][i] = stg_res[(d * L + i) * T + tid];
+    } else if (!OWN || c == 1) {
 #pragma unroll
       for (int d = 0; d < D; ++d)
 #pragma unroll
