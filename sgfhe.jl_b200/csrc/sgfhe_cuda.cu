@@ -37,6 +37,7 @@ struct GateArgs {
   unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
   const uint64_t* pack_in;                      // F_PACK: [batch][m][2] wide polynomials, job g multiplies poly g with key row g
   const int64_t* pack_draws;                    // F_PACK: NULL or [batch][m][2]
+  int* work_counter;                            // NULL (gate g = blockIdx.x + k gridDim.x) or a zeroed device counter: CTAs take the next gate when they finish one
   int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
 
@@ -194,14 +195,11 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const int idx = tid + (it0 + d) * T;
-        uint32_t yc[L];
-#pragma unroll
-        for (int i = 0; i < L; ++i) yc[i] = yq[d][i];
+        sm4[idx] = crt_sum<0, L>(C, yq[d], 1);
         if (it0 + d + D < NIT) {
 #pragma unroll
           for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
         }
-        sm4[idx] = crt_sum<0, L>(C, yc, 1);
       }
     }
     constexpr int DS = OWN ? D : 0;                          // accumulator words of the first DS iterations: async copies
@@ -396,7 +394,15 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
     const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
     while (clock64() - t0 < wait) __nanosleep(256);
   }
-  for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
+  // Persistent CTAs.  SMs do not all run at the same pace (two dies, different distances to L2), so with a work counter
+  // a CTA takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
+  for (int g = blockIdx.x;;) {
+    if (A.work_counter) {
+      if (threadIdx.x == 0) sm[6 * m + 2] = (uint32_t)atomicAdd(A.work_counter, 1);
+      __syncthreads();
+      g = (int)sm[6 * m + 2];
+    }
+    if (g >= A.batch) break;
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
     const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
@@ -438,6 +444,7 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
                  A.out_xor + (size_t)g * (n + 1) * w, (A.flags & F_RAW) != 0);
     }
     __syncthreads();
+    if (!A.work_counter) g += gridDim.x;
   }
 }
 
@@ -746,7 +753,15 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
     while (clock64() - t0 < wait) __nanosleep(256);
   }
-  for (int g = blockIdx.x; g < A.batch; g += gridDim.x) {
+  // Persistent CTAs.  SMs do not all run at the same pace (two dies, different distances to L2), so with a work counter
+  // a CTA takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
+  for (int g = blockIdx.x;;) {
+    if (A.work_counter) {
+      if (threadIdx.x == 0) sm[6 * m + 2] = (uint32_t)atomicAdd(A.work_counter, 1);
+      __syncthreads();
+      g = (int)sm[6 * m + 2];
+    }
+    if (g >= A.batch) break;
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
     const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
@@ -788,6 +803,7 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
                  A.out_xor + (size_t)g * (n + 1) * w, (A.flags & F_RAW) != 0);
     }
     __syncthreads();
+    if (!A.work_counter) g += gridDim.x;
   }
   mbar_wait(bar, parity);                                // the table staged for a step that never runs
 }
@@ -1018,6 +1034,7 @@ struct sgfhe_ctx {
   uint8_t* d_scratch = nullptr; int scratch_ctas = 0;
   uint32_t* d_pm_scratch = nullptr; int pm_ctas = 0;
   uint64_t* d_io = nullptr; size_t io_capacity = 0;
+  int* d_counter = nullptr;                        // work counter of the persistent gate kernels
 };
 
 static void to_limbs(u128 v, uint32_t out[3]) { out[0] = (uint32_t)v; out[1] = (uint32_t)(v >> 32); out[2] = (uint32_t)(v >> 64); }
@@ -1252,7 +1269,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
 extern "C" int sgfhe_ctx_destroy(sgfhe_ctx* c) {
   if (!c) return SGFHE_OK;
   cudaSetDevice(c->device);
-  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch); cudaFree(c->d_io);
+  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch); cudaFree(c->d_io); cudaFree(c->d_counter);
   delete c;
   return SGFHE_OK;
 }
@@ -1380,6 +1397,11 @@ static int launch_gates(sgfhe_ctx* c, GateArgs& A, cudaStream_t st) {
   A.keyhat = c->d_keyhat; A.tw_f = c->d_tw_f; A.tw_i = c->d_tw_i;
   A.scratch = c->d_scratch; A.scratch_stride = c->scratch_stride;
   A.zres = c->d_scratch + (size_t)c->scratch_ctas * c->scratch_stride; A.zres_stride = c->zres_stride;
+  if (A.batch > grid) {                              // more gates than CTAs: dynamic distribution
+    if (!c->d_counter && cudaMalloc(&c->d_counter, sizeof(int)) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the work counter failed");
+    CK(cudaMemsetAsync(c->d_counter, 0, sizeof(int), st));
+    A.work_counter = c->d_counter;
+  }
   launch_bootstrap(c, grid, st, A);
   CK(cudaGetLastError());
   return SGFHE_OK;
