@@ -143,6 +143,27 @@ def test_bootstrap_gates_p64(env64, so, sg, use_rng):
             assert np.array_equal(o[g], r)
 
 
+def test_more_gates_than_resident_ctas_p64(env64, so, sg):
+    """a batch larger than the number of resident CTAs (dynamic gate distribution through the work counter, small-m
+    kernel): same rows as one-gate launches, every gate decrypts to the plaintext gate, run to run identical"""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    W = 3000
+    idx1 = np.arange(W) % 32
+    idx2 = 32 + (np.arange(W) * 7) % 32
+    l1, l2 = lwes[idx1], lwes[idx2]
+    o1 = sg.bootstrap_batch(bkey, None, l1, l2)
+    o2 = sg.bootstrap_batch(bkey, None, l1, l2)
+    small = sg.bootstrap_batch(bkey, None, l1[:32], l2[:32])
+    skb = np.asarray(sk, dtype=bool)
+    y1, y2 = bits[idx1].astype(np.int64), bits[idx2].astype(np.int64)
+    for a, b, s_, want in zip(o1, o2, small, (y1 & y2, y1 | y2, y1 ^ y2)):
+        assert np.array_equal(a, b)
+        assert np.array_equal(a[:32], s_)
+        assert np.array_equal(a[32:64], a[2432:2464])          # gates 32 + k and 2432 + k have the same inputs (2400 = 75 * 32, 7 * 2400 = 525 * 32)
+        b1 = (a[:, OP.n].astype(np.int64) - a[:, :OP.n][:, skb].astype(np.int64).sum(axis=1)) % OP.r
+        assert np.array_equal(((b1 + OP.Dr // 2) % OP.r) // OP.Dr, want)
+
+
 def test_bootstrap_is_deterministic_without_rng(env64, sg):
     """docs/src/manual.md:155-169"""
     P, OP, sk, key, bits, lwes, bkey = env64
