@@ -332,7 +332,7 @@ def run_ours(args) -> None:
         }
         # second half of BASELINE.json's metric: standalone NTT polymuls/s at this ring degree (both operands full size)
         try:
-            pb = 1024
+            pb = int(os.environ.get("SGFHE_PM_BATCH", "2368"))       # 16 products per SM: no partial wave for one or two products per CTA
             pa = torch.from_numpy((np.random.default_rng(7).integers(0, 1 << 62, size=(pb, P.m, 2), dtype=np.uint64) &
                                    np.array([0xFFFFFFFFFFFFFFFF, (1 << max(qbits - 65, 0)) - 1], np.uint64)).view(np.int64)).cuda()
             po = torch.empty_like(pa)

@@ -930,6 +930,166 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
   }
 }
 
+// Standalone products with the building blocks of the v4 bootstrap kernel (m >= 4096): one CTA multiplies TWO pairs of
+// operands at a time, so a prime is 4 forward + 2 inverse transforms, the same shape as a bootstrap step: top stages
+// in registers straight from the operands, warp-local shared-memory passes, the pointwise products fused between the
+// stride-1 forward and inverse passes, residues to scratch [LM][2][m], CRT lift at the end.
+template <int LOGM>
+__global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
+polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
+                  uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, uint32_t* scratch, int batch) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  using S4 = Shape4<LOGM>;
+  constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, LM = Shape<LOGM>::LM, SB = 6 * LOGM + 8;
+  const int tid = threadIdx.x;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint2* toptw = reinterpret_cast<uint2*>(sm + 6 * m + 4);
+  uint32_t* zres = scratch + (size_t)blockIdx.x * LM * 2 * m;
+  uint32_t parity = 0, pc = 0;
+  if (tid == 0) {
+    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage_table(tab, tw_f, m * 8, bar);
+  }
+  write_top_twiddles<R0>(toptw, tw_f, C.p[0]);
+  __syncthreads();
+  const int st = swz(tid);
+  const int npairs = (batch + 1) / 2;
+  for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
+    const int g0 = 2 * pr, g1 = (2 * pr + 1 < batch) ? 2 * pr + 1 : g0;     // an odd batch repeats its last product
+    // operand polynomial of buffer j: (a, b) of the first product, then of the second
+    auto operand = [&](int j) {
+      return reinterpret_cast<const ulonglong2*>(j & 1 ? b : a) + (size_t)(j & 2 ? g1 : g0) * m;
+    };
+    // Half a polynomial's operand words (8 coefficients per thread, 32 registers) are kept in flight: the second half is
+    // requested while the first is reduced, the next polynomial's first half while this one runs its top stages.
+    constexpr int H = R0 / 2;
+    ulonglong2 raw[H];
+    {
+      const ulonglong2* s0 = operand(2);
+#pragma unroll
+      for (int k = 0; k < H; ++k) raw[k] = s0[tid + k * T];
+    }
+#pragma unroll 1
+    for (int i = 0; i < LM; ++i, ++pc) {
+      const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
+      const uint2* top = toptw + (pc & 1) * 2 * R0;
+      // ---- operands -> centred residues -> top LR0 stages in registers -> shared memory (order 2,3,0,1, see gate_step_v4)
+#pragma unroll 1
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = (jj + 2) & 3;
+        const ulonglong2* sj = operand(j);
+        const ulonglong2* sn = operand((jj + 3) & 3);        // next polynomial (after the fourth: the first one again, next prime)
+        if (jj == 2) __syncthreads();                      // previous prime's residue store has left buffers 0,1
+        uint32_t x[R0];
+#pragma unroll
+        for (int k = 0; k < H; ++k) { x[k] = centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sj[tid + (k + H) * T]; }
+#pragma unroll
+        for (int k = 0; k < H; ++k) { x[k + H] = centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sn[tid + k * T]; }
+        fwd_block<LR0>(x, top, p, p2, z);
+#pragma unroll
+        for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
+      }
+      __syncthreads();
+      mbar_wait(bar, parity); parity ^= 1;
+      {
+        const int nxt = (i + 1 == LM) ? 0 : i + 1;
+        write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
+      }
+      pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
+      slice_sync<LOGM>();
+      pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
+      __syncwarp();
+      // ---- fused: stride-1 forward pass of the four operands, two pointwise products, stride-1 inverse pass
+      {
+        const uint32_t pinv = C.pinv_neg[i];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+          const int blk = block_of<LOGM>(tid, q), base = 8 * blk;
+          const int a0 = swz(base), a1 = a0 ^ 4;
+          uint2 w[7];
+          block_twiddles<true>(tab, m / 8, blk, p, w);
+          uint32_t y[2][8];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t u[8], v[8];
+            {
+              const uint4 v0 = *reinterpret_cast<const uint4*>(sm + (2 * c) * m + a0), v1 = *reinterpret_cast<const uint4*>(sm + (2 * c) * m + a1);
+              u[0] = v0.x; u[1] = v0.y; u[2] = v0.z; u[3] = v0.w; u[4] = v1.x; u[5] = v1.y; u[6] = v1.z; u[7] = v1.w;
+              const uint4 w0 = *reinterpret_cast<const uint4*>(sm + (2 * c + 1) * m + a0), w1 = *reinterpret_cast<const uint4*>(sm + (2 * c + 1) * m + a1);
+              v[0] = w0.x; v[1] = w0.y; v[2] = w0.z; v[3] = w0.w; v[4] = w1.x; v[5] = w1.y; v[6] = w1.z; v[7] = w1.w;
+            }
+            fwd_block<3>(u, w, p, p2, z);
+            fwd_block<3>(v, w, p, p2, z);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {                   // operands corrected to [0, 2p): product < 4 p^2, redc in [0, 2p)
+              const uint32_t ue = min(u[e], u[e] - p2), ve = min(v[e], v[e] - p2);
+              y[c][e] = redc((uint64_t)ue * ve, p, pinv);
+            }
+          }
+          uint2 wi[7];
+          block_twiddles<false>(tab, m / 8, blk, p, wi);
+          inv_block<3, true>(y[0], wi, p, p2, z);
+          inv_block<3, true>(y[1], wi, p, p2, z);
+          *reinterpret_cast<uint4*>(sm + a0) = make_uint4(y[0][0], y[0][1], y[0][2], y[0][3]);
+          *reinterpret_cast<uint4*>(sm + a1) = make_uint4(y[0][4], y[0][5], y[0][6], y[0][7]);
+          *reinterpret_cast<uint4*>(sm + m + a0) = make_uint4(y[1][0], y[1][1], y[1][2], y[1][3]);
+          *reinterpret_cast<uint4*>(sm + m + a1) = make_uint4(y[1][4], y[1][5], y[1][6], y[1][7]);
+        }
+      }
+      __syncwarp();
+      pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
+      slice_sync<LOGM>();
+      pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
+      __syncthreads();                                     // last reader of `tab` for this prime is done
+      if (tid == 0) stage_table(tab, tw_f + (size_t)((i + 1 == LM) ? 0 : i + 1) * m, m * 8, bar);
+      // ---- top inverse stages in registers + CRT pre-scaling (with the 2^32 of the Montgomery product) + store
+      {
+        const uint32_t sc = C.scale[1][i], scs = C.scale_sh[1][i], sw = C.scale_w1[i], sws = C.scale_w1_sh[i];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t x[R0];
+#pragma unroll
+          for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
+          inv_block_upper<LR0>(x, top + R0, p, p2, z);
+#pragma unroll
+          for (int k = 0; k < R0 / 2; ++k) {
+            const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
+            zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(s0, sc, scs, p), p);
+            zres[((size_t)i * 2 + c) * m + tid + (k + R0 / 2) * T] = csub(shoup_mul(d0, sw, sws, p), p);
+          }
+        }
+      }
+    }
+    // ---- CRT lift (each thread reads only residues it stored itself)
+    for (int c = 0; c < (g1 != g0 ? 2 : 1); ++c) {
+      uint64_t* o = out + (size_t)(c ? g1 : g0) * m * 2;
+      const uint32_t* zr = zres + (size_t)c * m;
+      constexpr int NIT = m / T, DP = 2;                    // residues of DP coefficients in flight
+      uint32_t yq[DP][LM];
+#pragma unroll
+      for (int d = 0; d < DP; ++d)
+#pragma unroll
+        for (int q = 0; q < LM; ++q) yq[d][q] = zr[(size_t)q * 2 * m + tid + d * T];
+#pragma unroll 1
+      for (int it0 = 0; it0 < NIT; it0 += DP) {
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          const int idx = tid + (it0 + d) * T;
+          const u96 zv = crt_lift<1, LM, SB>(C, yq[d], 1);
+          if (it0 + d + DP < NIT) {
+#pragma unroll
+            for (int q = 0; q < LM; ++q) yq[d][q] = zr[(size_t)q * 2 * m + idx + DP * T];
+          }
+          reinterpret_cast<ulonglong2*>(o)[idx] = make_ulonglong2((uint64_t)zv.x0 | ((uint64_t)zv.x1 << 32), zv.x2);
+        }
+      }
+    }
+    __syncthreads();                                       // buffers 2,3 of the next pair are written before its first barrier
+  }
+  mbar_wait(bar, parity);                                  // the table staged for a prime that never runs
+}
+
 // flatten_poly seam (src/utils.jl:253-264): a [m] wide -> out [2][m] wide residues mod Q
 __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a,
                                const int64_t* __restrict__ draws, uint64_t* __restrict__ out) {
@@ -1109,6 +1269,10 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
         const uint64_t psi_inv = h_powmod64(h_root_2m(p, hp.m), p - 2, p);
         const uint64_t sw = h_mulmod64(sc, h_powmod64(psi_inv, hp.m / 2, p), p);
         dc->scale_w[i] = (uint32_t)sw; dc->scale_w_sh[i] = (uint32_t)((sw << 32) / p);
+      } else {
+        const uint64_t psi_inv = h_powmod64(h_root_2m(p, hp.m), p - 2, p);
+        const uint64_t sw = h_mulmod64(sc, h_powmod64(psi_inv, hp.m / 2, p), p);
+        dc->scale_w1[i] = (uint32_t)sw; dc->scale_w1_sh[i] = (uint32_t)((sw << 32) / p);
       }
     }
   }
@@ -1152,7 +1316,8 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   if (c->use_v4) {
     SGFHE_DISPATCH_V4(c->hp.logm, {
       c->boot_threads = Shape4<LOGM_>::T;
-      e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+      e = cudaFuncSetAttribute(polymul_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_>, c->boot_threads, c->smem_bytes);
     });
     if (e != cudaSuccess) return e;
@@ -1195,6 +1360,12 @@ static void launch_key_transform(const sgfhe_ctx* c, int npolys, const uint64_t*
 }
 static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const uint64_t* a, const uint64_t* b, uint64_t* out,
                            int batch) {
+  if (c->use_v4 && !getenv("SGFHE_POLYMUL_V3")) {
+    SGFHE_DISPATCH_V4(c->hp.logm, (polymul_kernel_v4<LOGM_><<<grid, c->boot_threads, c->smem_bytes, st>>>(
+                                       c->dc, a, b, out, c->d_tw_f, c->d_pm_scratch, batch)));
+    ++g_launches;
+    return;
+  }
   SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 16 + 16, st>>>(
                                   c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch)));
   ++g_launches;
@@ -1706,11 +1877,12 @@ extern "C" int sgfhe_polymul_device(sgfhe_ctx* c, int32_t batch, const uint64_t*
   if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
   if (batch == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
-  const int cap = c->num_sms * 2;
-  const int grid = batch < cap ? batch : cap;
+  const bool v4 = c->use_v4 && !getenv("SGFHE_POLYMUL_V3");
+  const int cap = v4 ? c->num_sms : c->num_sms * 2, units = v4 ? (batch + 1) / 2 : batch;     // v4: one CTA per SM, two products at a time
+  const int grid = units < cap ? units : cap;
   if (grid > c->pm_ctas) {
     cudaFree(c->d_pm_scratch); c->d_pm_scratch = nullptr; c->pm_ctas = 0;
-    if (cudaMalloc(&c->d_pm_scratch, (size_t)grid * c->dc.LM * c->hp.m * sizeof(uint32_t)) != cudaSuccess)
+    if (cudaMalloc(&c->d_pm_scratch, (size_t)grid * c->dc.LM * 2 * c->hp.m * sizeof(uint32_t)) != cudaSuccess)
       return fail(SGFHE_ERR_NOMEM, "cudaMalloc of polymul scratch failed");
     c->pm_ctas = grid;
   }
