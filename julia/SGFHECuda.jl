@@ -85,3 +85,32 @@ function bootstrap(ctx::CudaContext, bkey::BootstrapKey, rng::Union{AbstractRNG,
     a, o, x = bootstrap(ctx, bkey, rng, [enc_bit1], [enc_bit2])
     a[1], o[1], x[1]
 end
+
+"""
+`split_ciphertext` (src/fhe.jl:287-290) on the GPU: the n `EncryptedBit`s of one RLWE ciphertext.
+"""
+function split_ciphertext(ctx::CudaContext, ct::Union{Ciphertext, PackedCiphertext})
+    p = ctx.params
+    N = length(ct.rlwe.a.coeffs)
+    a = UInt64[value(x) for x in ct.rlwe.a.coeffs]
+    b = UInt64[value(x) for x in ct.rlwe.b.coeffs]
+    lwes = Array{UInt64}(undef, p.n + 1, p.n)              # column-major = C [n][n+1]
+    _check(ccall((:sgfhe_split_ciphertext, libsgfhe), Cint,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{UInt64}, Ptr{UInt64}, Ptr{UInt64}), ctx.handle, 1, N, a, b, lwes))
+    tp = type_r(p)
+    [EncryptedBit(LWE([tp(lwes[k, i], DarkIntegers._verbatim) for k in 1:p.n], tp(lwes[p.n + 1, i], DarkIntegers._verbatim)))
+     for i in 1:p.n]
+end
+
+"""
+`decrypt(key, ::EncryptedBit)` (src/fhe.jl:504-507) for a vector of encrypted bits on the GPU.
+"""
+function decrypt(ctx::CudaContext, key::PrivateKey, bits::AbstractVector{EncryptedBit})
+    p = ctx.params
+    l = hcat((_flat(b.lwe) for b in bits)...)
+    sk = UInt8[value(x) for x in key.key.coeffs]
+    out = Vector{UInt8}(undef, length(bits))
+    _check(ccall((:sgfhe_decrypt_bits, libsgfhe), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{UInt64}, Ptr{UInt8}, Ptr{UInt8}), ctx.handle, length(bits), l, sk, out))
+    convert.(Bool, out)                                    # InexactError for values > 1, as at src/fhe.jl:506
+end

@@ -22,6 +22,7 @@ struct DevConst {
   int L;                        // primes used by the bootstrap external product
   int LM;                       // primes used by a general product of two full-size operands
   int sbits;                    // bits(Q) - 1
+  int pm_uncentred;             // the LM-prime basis holds m Q^2 with the CRT margin: standalone products skip the centring
   uint32_t zero;                // always 0; a constant-bank operand ptxas cannot fold (forces 3-input IADD3 on the ALU pipe)
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
@@ -364,6 +365,16 @@ __device__ __forceinline__ uint32_t centred_mod(const DevConst& C, int i, uint64
   const bool upper = hi > C.Qhalf[1] || (hi == C.Qhalf[1] && lo > C.Qhalf[0]);                      // c > Q/2: c - Q
   const uint32_t tn = t - C.qmodp[i];
   return upper ? min(tn, tn + p) : t;
+}
+
+// canonical value c = lo + 2^64 hi of Z_Q as a residue mod p_i in [0, 4p) (the input range of the forward butterflies),
+// NOT centred: for products whose RNS basis has room for m Q^2 (DevConst::pm_uncentred)
+__device__ __forceinline__ uint32_t plain_mod(const DevConst& C, int i, uint64_t lo, uint64_t hi) {
+  const uint32_t p = C.p[i], p2 = 2 * p;
+  const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi;
+  uint32_t t = shoup_mul(w1, C.r32[i], C.r32_sh[i], p) + shoup_mul(w2, C.r64[i], C.r64_sh[i], p);   // [0, 4p)
+  t = min(t, t - p2);
+  return t + (w0 - (w0 >> 30) * p);                                                                  // [0, 4p)
 }
 
 // 128-bit limb helpers for the unreduced CRT sums

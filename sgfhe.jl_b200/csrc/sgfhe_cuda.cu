@@ -954,6 +954,7 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
   write_top_twiddles<R0>(toptw, tw_f, C.p[0]);
   __syncthreads();
   const int st = swz(tid);
+  const bool unc = C.pm_uncentred != 0;
   const int npairs = (batch + 1) / 2;
   for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) {
     const int g0 = 2 * pr, g1 = (2 * pr + 1 < batch) ? 2 * pr + 1 : g0;     // an odd batch repeats its last product
@@ -983,9 +984,9 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
         if (jj == 2) __syncthreads();                      // previous prime's residue store has left buffers 0,1
         uint32_t x[R0];
 #pragma unroll
-        for (int k = 0; k < H; ++k) { x[k] = centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sj[tid + (k + H) * T]; }
+        for (int k = 0; k < H; ++k) { x[k] = unc ? plain_mod(C, i, raw[k].x, raw[k].y) : centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sj[tid + (k + H) * T]; }
 #pragma unroll
-        for (int k = 0; k < H; ++k) { x[k + H] = centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sn[tid + k * T]; }
+        for (int k = 0; k < H; ++k) { x[k + H] = unc ? plain_mod(C, i, raw[k].x, raw[k].y) : centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sn[tid + k * T]; }
         fwd_block<LR0>(x, top, p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
@@ -1210,12 +1211,19 @@ static int choose_primes(double need_bits, const std::vector<uint32_t>& primes) 
 
 static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* twf, std::vector<uint2>* twi) {
   memset(dc, 0, sizeof *dc);
+  bool dc_uncentred_ok = false;
   const std::vector<uint32_t> primes = h_rns_primes(MAXP);
   const double lq = log2((double)hp.Q), lB = log2((double)hp.B), lm = hp.logm;
   // |sum of 4 m products digit * centred key| < 4 m (2B+1) Q/2 ; +1 sign bit, +4 bits for the CRT rounding margin
   const int L = choose_primes(2 + lm + (lB + 1.001) + (lq - 1) + 1 + 4, primes);
   const int LM = choose_primes(lm + 2 * (lq - 1) + 1 + 4, primes);
   if (L < 0 || LM < 0) return -1;
+  {
+    double have = 0;
+    for (int k = 0; k < LM; ++k) have += log2((double)primes[k]);
+    dc_uncentred_ok = have >= lm + 2 * lq + 5;             // m Q^2 < P / 32 without centring the operands
+  }
+  dc->pm_uncentred = dc_uncentred_ok ? 1 : 0;
   dc->n = hp.n; dc->m = hp.m; dc->logm = hp.logm; dc->logr = hp.logr; dc->kB = hp.kB; dc->L = L; dc->LM = LM;
   dc->sbits = h_bits(hp.Q) - 1;
   dc->Q = hp.Q; dc->DQ = hp.DQ; dc->B = hp.B;
