@@ -68,7 +68,7 @@ def main():
         w = (qbits + 31) // 32
         modmuls = 3 * (m // 2) * (m.bit_length() - 1) + m                     # standalone product
         rate = args.batch / (ms / 1e3)
-        print(json.dumps({"kernel": "polymul_kernel", "workload": f"Params({n}): m={m}, {qbits}-bit Q, batch {args.batch}, both operands full size",
+        print(json.dumps({"kernel": "polymul_kernel_v4" if m >= 4096 else "polymul_kernel", "workload": f"Params({n}): m={m}, {qbits}-bit Q, batch {args.batch}, both operands full size",
                           "polymuls_per_s": rate, "ms": ms,
                           "roofline": {"bound": "int32-pipe", "achieved": rate * modmuls * (2 * w * w + w) / 1e9, "peak": imad / 1e9, "unit": "GIMAD/s",
                                        "frac": rate * modmuls * (2 * w * w + w) / imad},
