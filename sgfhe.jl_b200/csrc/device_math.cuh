@@ -41,6 +41,7 @@ struct DevConst {
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
   uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t scale_w1[MAXP], scale_w1_sh[MAXP];   // the same for scale[1] (standalone products)
+  uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
   uint32_t crt_c[2][MAXP][3];               // (P/p_i) mod Q, 32-bit limbs
   uint32_t negP[2][3];                      // (-P) mod Q
 };

@@ -468,7 +468,6 @@ struct Shape4 {
   static constexpr int L = Shape<LOGM>::L;
 };
 
-__device__ __forceinline__ uint2 tw_neg(uint2 w, uint32_t p) { return make_uint2(p - w.x, ~w.y); }
 
 // Between the top stages and the last inverse pass every element with index bits [9, LOGM) fixed is touched only by
 // the 64 consecutive threads that own that 512-element slice, so the stride-64 <-> stride-8 hand-over needs a
@@ -560,21 +559,10 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   }
 }
 
-// uniform top-stage twiddles of one prime into shared memory: fwd[k-1] = tw[k], inv[k-1] derived, k in [1, R0)
-template <int R0>
-__device__ __forceinline__ void write_top_twiddles(uint2* slot, const uint2* __restrict__ gtw, uint32_t p) {
-  const int k = threadIdx.x;
-  if (k >= 1 && k < R0) {
-    slot[k - 1] = __ldg(&gtw[k]);
-    const int lvl = 1 << (31 - __clz(k));
-    slot[R0 + k - 1] = tw_neg(__ldg(&gtw[lvl + ((k - lvl) ^ (lvl - 1))]), p);
-  }
-}
-
 template <int LOGM>
 __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                              const uint2* __restrict__ tw_f, const int64_t* __restrict__ draws_next, int u, bool ext,
-                             bool decompose_next, uint2* tab, uint64_t* bar, uint2* toptw, uint32_t& parity, uint32_t& pc,
+                             bool decompose_next, uint2* tab, uint64_t* bar, uint32_t& parity,
                              unsigned long long* timing) {
   using S4 = Shape4<LOGM>;
   constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, L = S4::L;
@@ -588,9 +576,8 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll
   for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
 #pragma unroll 1
-  for (int i = 0; i < L; ++i, ++pc) {
+  for (int i = 0; i < L; ++i) {
     const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
-    const uint2* top = toptw + (pc & 1) * 2 * R0;        // [0,R0): forward, [R0,2R0): inverse top-stage twiddles
     // ---- P0: digits -> residues -> top LR0 stages in registers -> shared memory (register double buffered) ----
     {
       const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
@@ -606,20 +593,13 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
         uint32_t x[R0];
 #pragma unroll
         for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[jj & 1][k], dh[jj & 1][k], mu, negc, p);
-        fwd_block<LR0>(x, top, p, p2, z);
+        fwd_block<LR0>(x, C.topf[i], p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
       }
     }
     __syncthreads();
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
-    {
-      // Top-stage twiddles of the NEXT prime into the other slot.  Its last readers (the previous prime's top inverse
-      // stages) are behind the barrier above; the barrier after the inverse passes publishes it to every warp before the
-      // next digit load reads it.  (Written after that barrier it would race with warps that run ahead of warp 0.)
-      const int nxt = (i + 1 == L) ? 0 : i + 1;
-      write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
-    }
     SGFHE_TICK(0);
     pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
     slice_sync<LOGM>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
@@ -714,7 +694,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
         uint32_t x[R0];
 #pragma unroll
         for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
-        inv_block_upper<LR0>(x, top + R0, p, p2, z);
+        inv_block_upper<LR0>(x, C.topi[i], p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0 / 2; ++k) {
           const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
@@ -739,13 +719,11 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
   const int n = C.n;
   uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
-  uint2* toptw = reinterpret_cast<uint2*>(sm + 6 * m + 4);           // [2 slots][fwd R0 | inv R0]
-  uint32_t parity = 0, pc = 0;
+  uint32_t parity = 0;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage_table(tab, A.tw_f, m * 8, bar);
   }
-  write_top_twiddles<S4::R0>(toptw, A.tw_f, C.p[0]);
   __syncthreads();
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
@@ -788,7 +766,7 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
       const bool more = k + 1 < k_end;
       gate_step_v4<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f,
                          (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
-                         tab, bar, toptw, parity, pc, blockIdx.x == 0 ? A.timing : nullptr);
+                         tab, bar, parity, blockIdx.x == 0 ? A.timing : nullptr);
     }
     if (A.trace) {
       uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
@@ -944,14 +922,12 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
   const int tid = threadIdx.x;
   uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
-  uint2* toptw = reinterpret_cast<uint2*>(sm + 6 * m + 4);
   uint32_t* zres = scratch + (size_t)blockIdx.x * LM * 2 * m;
-  uint32_t parity = 0, pc = 0;
+  uint32_t parity = 0;
   if (tid == 0) {
     mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage_table(tab, tw_f, m * 8, bar);
   }
-  write_top_twiddles<R0>(toptw, tw_f, C.p[0]);
   __syncthreads();
   const int st = swz(tid);
   const bool unc = C.pm_uncentred != 0;
@@ -972,9 +948,8 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
       for (int k = 0; k < H; ++k) raw[k] = s0[tid + k * T];
     }
 #pragma unroll 1
-    for (int i = 0; i < LM; ++i, ++pc) {
+    for (int i = 0; i < LM; ++i) {
       const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
-      const uint2* top = toptw + (pc & 1) * 2 * R0;
       // ---- operands -> centred residues -> top LR0 stages in registers -> shared memory (order 2,3,0,1, see gate_step_v4)
 #pragma unroll 1
       for (int jj = 0; jj < 4; ++jj) {
@@ -987,16 +962,12 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
         for (int k = 0; k < H; ++k) { x[k] = unc ? plain_mod(C, i, raw[k].x, raw[k].y) : centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sj[tid + (k + H) * T]; }
 #pragma unroll
         for (int k = 0; k < H; ++k) { x[k + H] = unc ? plain_mod(C, i, raw[k].x, raw[k].y) : centred_mod(C, i, raw[k].x, raw[k].y); raw[k] = sn[tid + k * T]; }
-        fwd_block<LR0>(x, top, p, p2, z);
+        fwd_block<LR0>(x, C.topf[i], p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
       }
       __syncthreads();
       mbar_wait(bar, parity); parity ^= 1;
-      {
-        const int nxt = (i + 1 == LM) ? 0 : i + 1;
-        write_top_twiddles<R0>(toptw + ((pc + 1) & 1) * 2 * R0, tw_f + (size_t)nxt * m, C.p[nxt]);
-      }
       pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
       slice_sync<LOGM>();
       pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
@@ -1052,7 +1023,7 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
           uint32_t x[R0];
 #pragma unroll
           for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
-          inv_block_upper<LR0>(x, top + R0, p, p2, z);
+          inv_block_upper<LR0>(x, C.topi[i], p, p2, z);
 #pragma unroll
           for (int k = 0; k < R0 / 2; ++k) {
             const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
@@ -1296,6 +1267,14 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       const int r = h_bitrev(k, hp.logm);
       (*twf)[(size_t)i * m + k] = make_uint2((uint32_t)pf[r], (uint32_t)((pf[r] << 32) / p));
       (*twi)[(size_t)i * m + k] = make_uint2((uint32_t)pi[r], (uint32_t)((pi[r] << 32) / p));
+    }
+    // top-stage twiddles of the v4 kernels (constant bank): tw[k] and its inverse, the negated mirrored forward entry
+    const int r0 = hp.logm % 3 == 1 ? 16 : 8;
+    for (int k = 1; k < r0 && hp.logm >= 12; ++k) {
+      int lvl = 1; while (2 * lvl <= k) lvl *= 2;
+      const uint2 f = (*twf)[(size_t)i * m + k], mir = (*twf)[(size_t)i * m + lvl + ((k - lvl) ^ (lvl - 1))];
+      dc->topf[i][k - 1] = f;
+      dc->topi[i][k - 1] = make_uint2((uint32_t)p - mir.x, ~mir.y);
     }
   }
   return 0;
