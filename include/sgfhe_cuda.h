@@ -83,7 +83,9 @@ int sgfhe_bootstrap_batch(sgfhe_ctx* ctx, int32_t batch, const uint64_t* lwe1, c
                           const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor);
 
 /* Same, all six buffers already in device memory of ctx's device (draws may be NULL).
- * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream). */
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).  Launches on one context must not
+ * overlap in time (the per-gate scratch and the work counter belong to the context): use one stream per context, or one
+ * context per stream. */
 int sgfhe_bootstrap_batch_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* d_lwe1,
                                  const uint64_t* d_lwe2, const int64_t* d_draws, uint64_t* d_out_and,
                                  uint64_t* d_out_or, uint64_t* d_out_xor, void* stream);
