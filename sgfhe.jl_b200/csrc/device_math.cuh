@@ -37,8 +37,8 @@ struct DevConst {
   uint32_t r32_sh[MAXP], r64_sh[MAXP];      // their Shoup companions
   uint64_t Qhalf[2];                        // floor(Q / 2) as (lo, hi)
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
-  uint32_t dig_negc[MAXP];                  // p - (2^46 mod p)
-  uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: m^-1 (P_L/p)^-1 ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
+  uint32_t dig_negc[MAXP];                  // p - (2^46 mod p) - 4p (mod 2^32), see digit_mod
+  uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: -m^-1 (P_L/p)^-1 (digits are transformed negated) ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
   uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t scale_w1[MAXP], scale_w1_sh[MAXP];   // the same for scale[1] (standalone products)
   uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
@@ -348,9 +348,12 @@ __device__ __forceinline__ u96 from_offset_form(const DevConst& C, u96 a) { retu
 
 // Signed digits (|d| < 2^46) are stored biased, dp = d + 2^46, as two words: lo = dp mod 2^32, hi = dp >> 18.
 __device__ __forceinline__ void digit_words(uint64_t dp, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18); }
-// residue of the digit mod p in [0,3p): mu = floor(2^50 / p), negc = p - (2^46 mod p)
-__device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t mu, uint32_t negc, uint32_t p) {
-  return lo - __umulhi(hi, mu) * p + negc;
+// residue of the NEGATED digit mod p in (p, 4p]: mu = floor(2^50 / p), negc4 = p - (2^46 mod p) - 4p (mod 2^32).
+// q p - (lo + negc4) is one IMAD with a negated addend; lo - q p + negc would need an extra register move to negate q.
+// All four digit polynomials change sign together, which the CRT pre-scaling constants of the bootstrap basis undo
+// (scale[0], scale_w are stored negated).
+__device__ __forceinline__ uint32_t digit_mod(uint32_t lo, uint32_t hi, uint32_t mu, uint32_t negc4, uint32_t p) {
+  return __umulhi(hi, mu) * p - (lo + negc4);
 }
 
 // canonical value c = lo + 2^64 hi of Z_Q, centred to (-Q/2, Q/2], as a residue mod p_i in [0,p).

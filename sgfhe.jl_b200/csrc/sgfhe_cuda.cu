@@ -1228,7 +1228,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     if (5ull * ((1u << 30) - p) >= (1u << 30)) return -1;                  // centred_mod's reduction of the low word
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
-    dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p);
+    dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p) - 4u * p;      // wraps mod 2^32 on purpose
   }
   for (int basis = 0; basis < 2; ++basis) {
     const int K = basis == 0 ? L : LM;
@@ -1242,6 +1242,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       to_limbs(c, dc->crt_c[basis][i]);
       uint64_t sc = h_mulmod64(h_powmod64(cp, p - 2, p), h_powmod64((uint64_t)hp.m % p, p - 2, p), p);
       if (basis == 1) sc = h_mulmod64(sc, dc->r32[i], p);
+      else sc = (p - sc) % p;                              // digit_mod yields the negated digits
       dc->scale[basis][i] = (uint32_t)sc;
       dc->scale_sh[basis][i] = (uint32_t)((sc << 32) / p);
       if (basis == 0) {                                   // psi^(-m/2) = (psi^-1)^(m/2)
