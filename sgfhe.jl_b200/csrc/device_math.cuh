@@ -42,8 +42,8 @@ struct DevConst {
   uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t scale_w1[MAXP], scale_w1_sh[MAXP];   // the same for scale[1] (standalone products)
   uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
-  uint32_t crt_c[2][MAXP][3];               // (P/p_i) mod Q, 32-bit limbs
-  uint32_t negP[2][3];                      // (-P) mod Q
+  uint32_t crt_c[2][MAXP][3];               // [1]: (P/p_i) mod Q; [0]: -(P/p_i) mod Q (the bootstrap sums represent -z), 32-bit limbs
+  uint32_t negP[2][3];                      // [1]: (-P) mod Q; [0]: (+P) mod Q
 };
 
 // ---- swizzled shared-memory index: keeps every radix-8 pass bank-conflict free ---------------------

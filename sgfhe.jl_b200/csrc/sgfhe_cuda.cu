@@ -115,17 +115,18 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
     for (int d = 0; d < D; ++d) {
       const int j = tid + (it0 + d) * T;
       uint4 V;
+      // sm4 holds S' = -z (unreduced, 0 <= S' < KQ): the bootstrap basis' CRT constants are stored negated
       if (EXT) {
-        V = add128(sm4[j], OFF);
+        V = add128(sub128(KQ, sm4[j]), OFF);
       } else {
         const u96 a = aq[d];
         if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
         const int src = (j - u) & (2 * m - 1);
-        const uint4 zr = sm4[src & (m - 1)];
-        const uint4 nz = sub128(KQ, zr);                              // x^u z wraps with a sign flip
-        const bool neg = src >= m;
-        const uint4 zs = make_uint4(neg ? nz.x : zr.x, neg ? nz.y : zr.y, neg ? nz.z : zr.z, neg ? nz.w : zr.w);
-        V = add128(add128(make_uint4(a.x0, a.x1, a.x2, 0), sub128(KQ, sm4[j])), zs);   // < Q + 2 KQ < 2^35 Q
+        const uint4 nr = sm4[src & (m - 1)];                          // -z[j-u]
+        const uint4 pr = sub128(KQ, nr);                              // +z[j-u]
+        const bool neg = src >= m;                                    // x^u z wraps with a sign flip
+        const uint4 zs = make_uint4(neg ? nr.x : pr.x, neg ? nr.y : pr.y, neg ? nr.z : pr.z, neg ? nr.w : pr.w);
+        V = add128(add128(make_uint4(a.x0, a.x1, a.x2, 0), sm4[j]), zs);   // acc - z[j] +- z[j-u]  < Q + 2 KQ < 2^35 Q
       }
       const u96 res = barrett96<SB>(C, V);
       st96(acc, m, j, res);
@@ -1234,12 +1235,13 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     const int K = basis == 0 ? L : LM;
     u128 Pm = 1 % hp.Q;
     for (int i = 0; i < K; ++i) Pm = h_mulmod(Pm, primes[i], hp.Q);
-    to_limbs((hp.Q - Pm) % hp.Q, dc->negP[basis]);
+    // basis 0 (bootstrap): the sums represent -z, so its constants are negated: (+P) mod Q and -(P/p_i) mod Q
+    to_limbs(basis == 0 ? Pm : (hp.Q - Pm) % hp.Q, dc->negP[basis]);
     for (int i = 0; i < K; ++i) {
       const uint32_t p = primes[i];
       u128 c = 1; uint64_t cp = 1;
       for (int j = 0; j < K; ++j) if (j != i) { c = h_mulmod(c, primes[j], hp.Q); cp = h_mulmod64(cp, primes[j] % p, p); }
-      to_limbs(c, dc->crt_c[basis][i]);
+      to_limbs(basis == 0 ? (hp.Q - c) % hp.Q : c, dc->crt_c[basis][i]);
       uint64_t sc = h_mulmod64(h_powmod64(cp, p - 2, p), h_powmod64((uint64_t)hp.m % p, p - 2, p), p);
       if (basis == 1) sc = h_mulmod64(sc, dc->r32[i], p);
       else sc = (p - sc) % p;                              // digit_mod yields the negated digits
