@@ -675,15 +675,15 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
     slice_sync<LOGM>();
     pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
+    if (i + 1 < L) {                                     // next prime's first digit words: requested before the barrier, so a
+#pragma unroll                                           // warp that arrives early waits with its loads already in flight
+      for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+    }
     __syncthreads();                                     // last reader of `tab` for this prime is done
     {
       // TMA: next prime's forward table under the store phase.  After the last prime the table region serves the
       // CRT/update phases as a staging area; prime 0's table for the next step is requested after them.
       if (tid == 0 && i + 1 < L) stage_table(tab, tw_f + (size_t)(i + 1) * m, m * 8, bar);
-    }
-    if (i + 1 < L) {                                     // next prime's first digit words, requested under the store phase
-#pragma unroll
-      for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
     }
     SGFHE_TICK(3);
     // ---- top inverse stages in registers + CRT pre-scaling + store of the residues --------------------------
