@@ -522,9 +522,21 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
     const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
     uint2 w[7];
     block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
+    // swz(base + (j << B)) with the structure of the swizzle spelled out: only bits 2..4 depend on j through an XOR, the
+    // rest is an immediate offset of the load / store
     int off[8];
+    if constexpr (B == 6) {                               // bits 6,7 = j & 3 go to bits 3,4; bit 5 (of base) to bit 2
+      const int b0 = swz(base);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) off[j] = swz(base + (j << B));
+      for (int j = 0; j < 8; ++j) off[j] = (b0 ^ ((j & 3) << 3)) + (j << 6);
+    } else if constexpr (B == 3) {                        // bits 3,4 = j & 3 meet bits 6,7 of base; bit 5 = j >> 2 goes to bit 2
+      const int c = (base >> 6) & 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) off[j] = ((base + (((j & 3) ^ c) << 3)) ^ ((j >> 2) << 2)) + ((j >> 2) << 5);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) off[j] = swz(base + (j << B));
+    }
 #pragma unroll
     for (int poly = 0; poly < NPOLY; ++poly) {
       uint32_t* s = sm + poly * M;
