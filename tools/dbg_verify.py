@@ -1,3 +1,8 @@
+"""Determinism / correctness probe for large batches: tools/dbg_verify.py <batch>
+
+Runs Params(1024) bootstrap_batch twice on the same inputs, lists gates whose outputs differ between the runs and gates
+that decrypt to the wrong AND / OR / XOR.  (Found the barrier-less twiddle publication that only showed up when the
+persistent CTAs had drifted apart, i.e. at batches of several waves.)"""
 import os, sys, numpy as np, ctypes as C
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
 import importlib
