@@ -457,7 +457,12 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
 //     key tile streams from L2 underneath butterflies instead of in a phase of its own;
 //   * the last inverse pass runs the top stages in registers and stores CRT-ready residues straight to HBM/L2;
 //   * only the FORWARD twiddle table is staged (TMA, one prime ahead): psi^-bitrev(2^l+g) = -psi^bitrev(2^l+(g^(2^l-1))),
-//     so every inverse twiddle is the negation of a mirrored forward entry.
+//     so the inverse passes read the mirrored forward entries and fold the sign into the butterfly; the twiddles of the
+//     top stages (the same for every thread) are kernel parameters, i.e. constant-bank operands;
+//   * at m = 8192 every warp owns one 512-point slice between the top stages (warp-level synchronisation only), a lane
+//     works on two adjacent radix-8 blocks (64-bit shared-memory accesses);
+//   * the CRT sums stay unreduced until the accumulator update (one Barrett step per coefficient, FP64-assisted), the first
+//     loads of the tail arrive by cp.async in the then idle twiddle-table region.
 // =========================================================================================================
 template <int LOGM>
 struct Shape4 {
@@ -1418,7 +1423,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
   }
   const int m = hp.m;
-  c->smem_bytes = (size_t)24 * m + 16 + 1024;                // 4 NTT buffers + staged twiddle table + mbarrier + top-stage twiddles
+  c->smem_bytes = (size_t)24 * m + 16 + 1024;                // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare)
   int occ = 0;
   CK(configure_kernels(c, &occ));
   {
