@@ -44,6 +44,9 @@ struct DevConst {
   uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
   uint32_t crt_c[2][MAXP][3];               // [1]: (P/p_i) mod Q; [0]: -(P/p_i) mod Q (the bootstrap sums represent -z), 32-bit limbs
   uint32_t negP[2][3];                      // [1]: (-P) mod Q; [0]: (+P) mod Q
+  // FP64 head of the v4 bootstrap kernel (head_stage1_f64): p, 1/p, the stage-1 twiddle psi^(m/2), its quotient w/p and
+  // the conversion constant 1.5 2^52 + 2p, all as doubles
+  double hp_p[MAXP], hp_pinv[MAXP], hp_w[MAXP], hp_wp[MAXP], hp_c[MAXP];
 };
 
 // ---- swizzled shared-memory index: keeps every radix-8 pass bank-conflict free ---------------------
@@ -111,6 +114,45 @@ __device__ __forceinline__ void inv_block(uint32_t (&x)[1 << LOGR], const uint2*
         if (NEGW) gs_bfly_negw(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
         else gs_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
       }
+  }
+}
+
+// fwd_block without its first level (l = 0): the caller has already run it (head_stage1_f64)
+template <int LOGR>
+__device__ __forceinline__ void fwd_block_tail(uint32_t (&x)[1 << LOGR], const uint2* w, uint32_t p, uint32_t p2, uint32_t z) {
+  constexpr int R = 1 << LOGR;
+#pragma unroll
+  for (int l = 1; l < LOGR; ++l) {
+    const int half = R >> (l + 1);
+#pragma unroll
+    for (int g = 0; g < (1 << l); ++g)
+#pragma unroll
+      for (int k = 0; k < half; ++k) ct_bfly(x[g * 2 * half + k], x[g * 2 * half + k + half], w[(1 << l) - 1 + g], p, p2, z);
+  }
+}
+
+// First forward stage of a digit polynomial on the FP64 pipe (idle otherwise; DFMA issues at the IMAD rate).
+// d[k] are signed digits (|d| < 2^46) held exactly in doubles; pairs (k, k + R/2) with the single stage-1 twiddle w:
+//   t  = d[k+R/2] w mod p, centred:  h + l = d w exactly (h = fl(d w), l = fma(d, w, -h)), q = rint(d (w/p)) by the
+//        1.5 2^52 trick, t = fma(-q, p, h) + l  -- both exact (integers below 2^53), |t| <= (1/2 + 2^-7) p;
+//   ra = d[k] mod p, centred, the same way;  x = ra + t + 2p, y = ra - t + 2p land in (p/2, 7p/2), inside [0, 4p), the
+//   input range of the integer butterflies.  Adding 1.5 2^52 leaves the integer in the low word of the double.
+// Replaces per pair 2 digit reductions + 1 Harvey butterfly (10.6 FMA-heavy slots) by 12 FP64 instructions.
+template <int R>
+__device__ __forceinline__ void head_stage1_f64(const double (&d)[R], uint32_t (&x)[R], double p, double pinv, double w,
+                                                double wp, double cm) {
+  constexpr double M = 6755399441055744.0;              // 1.5 2^52
+#pragma unroll
+  for (int k = 0; k < R / 2; ++k) {
+    const double a = d[k], b = d[k + R / 2];
+    const double h = __dmul_rn(b, w);
+    const double l = __fma_rn(b, w, -h);
+    const double q = __dadd_rn(__fma_rn(b, wp, M), -M);
+    const double t = __dadd_rn(__fma_rn(-q, p, h), l);
+    const double qa = __dadd_rn(__fma_rn(a, pinv, M), -M);
+    const double rc = __dadd_rn(__fma_rn(-qa, p, a), cm);
+    x[k] = (uint32_t)__double2loint(__dadd_rn(rc, t));
+    x[k + R / 2] = (uint32_t)__double2loint(__dadd_rn(rc, -t));
   }
 }
 
@@ -348,6 +390,10 @@ __device__ __forceinline__ u96 from_offset_form(const DevConst& C, u96 a) { retu
 
 // Signed digits (|d| < 2^46) are stored biased, dp = d + 2^46, as two words: lo = dp mod 2^32, hi = dp >> 18.
 __device__ __forceinline__ void digit_words(uint64_t dp, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18); }
+// the NEGATED digit as a double (exact): bits 0x433 | dp are 2^52 + dp, and (2^52 + 2^46) - (2^52 + dp) = -d
+__device__ __forceinline__ double digit_f64(uint64_t dp) {
+  return __dadd_rn(4573968371548160.0, -__hiloint2double((int)(0x43300000u | (uint32_t)(dp >> 32)), (int)(uint32_t)dp));
+}
 // residue of the NEGATED digit mod p in (p, 4p]: mu = floor(2^50 / p), negc4 = p - (2^46 mod p) - 4p (mod 2^32).
 // q p - (lo + negc4) is one IMAD with a negated addend; lo - q p + negc would need an extra register move to negate q.
 // All four digit polynomials change sign together, which the CRT pre-scaling constants of the bootstrap basis undo

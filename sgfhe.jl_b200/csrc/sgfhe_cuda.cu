@@ -8,6 +8,7 @@
 #include "device_math.cuh"
 #include "host_math.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -43,12 +44,13 @@ struct GateArgs {
 
 // acc: the accumulator (a, b) in OFFSET FORM x + offs mod Q (device_math.cuh), limb-major; dig: the biased digit words
 // (dp mod 2^32, dp >> 18) of its gadget decomposition; zres: CRT-ready residues of the two product polynomials.
-struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; uint32_t* zres; };
+struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; double* digd; uint32_t* zres; };
 __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   Scratch s;
   s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
   s.diglo = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);       // [4][m]
   s.dighi = reinterpret_cast<uint32_t*>(base + (size_t)40 * m);       // [4][m]
+  s.digd = reinterpret_cast<double*>(base + (size_t)24 * m);          // [4][m] negated digits as doubles (FP64 head; same bytes as diglo + dighi)
   s.zres = reinterpret_cast<uint32_t*>(zbase);                        // [L][2][m]
   return s;
 }
@@ -83,7 +85,7 @@ __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
 }
 
 // gadget decomposition of accumulator polynomial c (src/utils.jl:253-264) into S.dig[2c], S.dig[2c+1]
-template <int LOGM>
+template <int LOGM, bool F64>
 __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch& S, int c, const int64_t* __restrict__ draws) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1;
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
@@ -91,8 +93,11 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
     uint64_t dp0, dp1;
     if (draws) decompose_off_rand<KB>(C, v, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], dp0, dp1);
     else decompose_off<KB>(C, v, dp0, dp1);
-    digit_words(dp0, S.diglo[(2 * c) * m + idx], S.dighi[(2 * c) * m + idx]);
-    digit_words(dp1, S.diglo[(2 * c + 1) * m + idx], S.dighi[(2 * c + 1) * m + idx]);
+    if (F64) { S.digd[(2 * c) * m + idx] = digit_f64(dp0); S.digd[(2 * c + 1) * m + idx] = digit_f64(dp1); }
+    else {
+      digit_words(dp0, S.diglo[(2 * c) * m + idx], S.dighi[(2 * c) * m + idx]);
+      digit_words(dp1, S.diglo[(2 * c + 1) * m + idx], S.dighi[(2 * c + 1) * m + idx]);
+    }
   }
 }
 
@@ -100,7 +105,7 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
 //   EXT  (external-product seam): acc = z;   otherwise acc += x^u z - z  (mul_by_xj_minus_one, src/fhe.jl:554-556, applied
 //   to the product), evaluated on the unreduced CRT sums as V = acc + (KQ - S[j]) + (S[j-u] or KQ - S[j-u]) with ONE Barrett
 //   reduction; DEC: fused with the next step's gadget decomposition (RAND: with the caller's draws).
-template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND>
+template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND, bool F64>
 __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S, const uint4* sm4, int c,
                                             const int64_t* __restrict__ draws_next, int u, u96 (&aq)[D]) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1, SB = 6 * LOGM + 8;
@@ -134,8 +139,11 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
         uint64_t dp0, dp1;
         if (RAND) decompose_off_rand<KB>(C, res, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], dp0, dp1);
         else decompose_off<KB>(C, res, dp0, dp1);
-        digit_words(dp0, S.diglo[(2 * c) * m + j], S.dighi[(2 * c) * m + j]);
-        digit_words(dp1, S.diglo[(2 * c + 1) * m + j], S.dighi[(2 * c + 1) * m + j]);
+        if (F64) { S.digd[(2 * c) * m + j] = digit_f64(dp0); S.digd[(2 * c + 1) * m + j] = digit_f64(dp1); }
+        else {
+          digit_words(dp0, S.diglo[(2 * c) * m + j], S.dighi[(2 * c) * m + j]);
+          digit_words(dp1, S.diglo[(2 * c + 1) * m + j], S.dighi[(2 * c + 1) * m + j]);
+        }
       }
     }
   }
@@ -145,7 +153,7 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
 // shared memory, then update_poly.  Every loop reads data written a whole step ago (largely evicted to HBM), so D
 // iterations of loads stay in flight and the first loads of each loop are issued one phase early, across the barriers.
 // OWN: each thread reads only residues it stored itself (v4 kernel), so those loads may precede the entry barrier.
-template <int LOGM, int T, bool OWN>
+template <int LOGM, int T, bool OWN, bool F64>
 __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
                                            const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
                                            unsigned long long* timing, long long& tprev) {
@@ -224,13 +232,13 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
       }
     }
     if (ext) {
-      if (!decompose_next) update_poly<LOGM, T, D, true, false, false>(C, S, sm4, c, nullptr, u, aq);
-      else if (draws_next) update_poly<LOGM, T, D, true, true, true>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, true, true, false>(C, S, sm4, c, nullptr, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, true, false, false, F64>(C, S, sm4, c, nullptr, u, aq);
+      else if (draws_next) update_poly<LOGM, T, D, true, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, true, true, false, F64>(C, S, sm4, c, nullptr, u, aq);
     } else {
-      if (!decompose_next) update_poly<LOGM, T, D, false, false, false>(C, S, sm4, c, nullptr, u, aq);
-      else if (draws_next) update_poly<LOGM, T, D, false, true, true>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, false, true, false>(C, S, sm4, c, nullptr, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, false, false, false, F64>(C, S, sm4, c, nullptr, u, aq);
+      else if (draws_next) update_poly<LOGM, T, D, false, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, false, true, false, F64>(C, S, sm4, c, nullptr, u, aq);
     }
     __syncthreads();
     SGFHE_TICK(6);
@@ -348,7 +356,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     __syncthreads();
     SGFHE_TICK(4);
   }
-  crt_update<LOGM, T, false>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
+  crt_update<LOGM, T, false, false>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
 
@@ -375,80 +383,6 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
     }
   }
 }
-
-// F_DECOMP: (re)compute S.dig from S.acc before the first step of this launch (set with F_INIT, and by the
-// trace / external-product seams whose accumulator arrives from a previous launch or from the host).
-template <int LOGM>
-__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
-bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
-  extern __shared__ __align__(16) uint32_t sm[];
-  constexpr int m = 1 << LOGM;
-  const int n = C.n;
-  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);                 // staged twiddle table of the current (prime, direction)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
-  uint32_t parity = 0;
-  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  __syncthreads();
-  const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
-  const uint64_t rmask = (1ull << C.logr) - 1;
-  if (A.stagger_cycles > 0) {
-    const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
-    while (clock64() - t0 < wait) __nanosleep(256);
-  }
-  // Persistent CTAs.  SMs do not all run at the same pace (two dies, different distances to L2), so with a work counter
-  // a CTA takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
-  for (int g = blockIdx.x;;) {
-    if (A.work_counter) {
-      if (threadIdx.x == 0) sm[6 * m + 2] = (uint32_t)atomicAdd(A.work_counter, 1);
-      __syncthreads();
-      g = (int)sm[6 * m + 2];
-    }
-    if (g >= A.batch) break;
-    const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
-    const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
-    const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
-    const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
-    if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
-    if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
-      u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
-      zero = to_offset_form(C, zero);
-      for (int e = threadIdx.x; e < m; e += blockDim.x) {
-        const uint64_t* src = A.pack_in + ((size_t)g * m + e) * 2;
-        u96 v; v.x0 = (uint32_t)src[0]; v.x1 = (uint32_t)(src[0] >> 32); v.x2 = (uint32_t)src[1];
-        st96(S.acc, m, e, zero); st96(S.acc + 3 * m, m, e, to_offset_form(C, v));
-      }
-    }
-    __syncthreads();
-    const int k_begin = pack ? g : A.step_begin, k_end = pack ? g + 1 : A.step_end;
-    if ((A.flags & F_DECOMP) && k_begin < k_end) {
-      decompose_poly<LOGM>(C, S, 0, pack ? nullptr : dr);
-      decompose_poly<LOGM>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
-    }
-    __syncthreads();
-    for (int k = k_begin; k < k_end; ++k) {
-      const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
-      const bool more = k + 1 < k_end;
-      gate_step<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f, A.tw_i,
-                      (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
-                      tab, bar, parity, blockIdx.x == 0 ? A.timing : nullptr);
-    }
-    if (A.trace) {
-      uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
-      for (int e = threadIdx.x; e < 2 * m; e += blockDim.x) {
-        const u96 v = from_offset_form(C, ld96(S.acc + (e / m) * 3 * m, m, e % m));
-        tr[2 * e] = (uint64_t)v.x0 | ((uint64_t)v.x1 << 32); tr[2 * e + 1] = v.x2;
-      }
-    }
-    if (A.flags & F_FINAL) {
-      const size_t w = (A.flags & F_RAW) ? 2 : 1;
-      gate_final(C, S, A.out_and + (size_t)g * (n + 1) * w, A.out_or + (size_t)g * (n + 1) * w,
-                 A.out_xor + (size_t)g * (n + 1) * w, (A.flags & F_RAW) != 0);
-    }
-    __syncthreads();
-    if (!A.work_counter) g += gridDim.x;
-  }
-}
-
 
 // =========================================================================================================
 // v4: fused-pass step for m >= 4096 (512 threads, up to 128 registers per thread).
@@ -577,7 +511,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   }
 }
 
-template <int LOGM>
+template <int LOGM, bool HF>
 __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                              const uint2* __restrict__ tw_f, const int64_t* __restrict__ draws_next, int u, bool ext,
                              bool decompose_next, uint2* tab, uint64_t* bar, uint32_t& parity,
@@ -590,28 +524,42 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
   // Digit words are prime independent.  Polynomials are processed in the order 2,3,0,1: buffers 2,3 are not read
   // by the previous prime's residue store, so that store overlaps the head of the next digit load.
   const int st = swz(tid);                               // swz(tid + k T) = swz(tid) + k T  (T is a multiple of 256)
-  uint32_t dl[2][R0], dh[2][R0];
+  // HF: the digits are doubles and the first stage runs on the FP64 pipe (head_stage1_f64); otherwise biased words
+  uint32_t dl[HF ? 1 : 2][HF ? 1 : R0], dh[HF ? 1 : 2][HF ? 1 : R0];
+  double dd[HF ? 2 : 1][HF ? R0 : 1];
 #pragma unroll
-  for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+  for (int k = 0; k < R0; ++k) {
+    if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * T];
+    else { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+  }
 #pragma unroll 1
   for (int i = 0; i < L; ++i) {
     const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
     // ---- P0: digits -> residues -> top LR0 stages in registers -> shared memory (register double buffered) ----
     {
       const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
+      const double fp = C.hp_p[i], fpinv = C.hp_pinv[i], fw = C.hp_w[i], fwp = C.hp_wp[i], fc = C.hp_c[i];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int j = (jj + 2) & 3;
         if (jj + 1 < 4) {
           const int jn = (jj + 3) & 3;
 #pragma unroll
-          for (int k = 0; k < R0; ++k) { dl[(jj + 1) & 1][k] = S.diglo[jn * m + tid + k * T]; dh[(jj + 1) & 1][k] = S.dighi[jn * m + tid + k * T]; }
+          for (int k = 0; k < R0; ++k) {
+            if constexpr (HF) dd[(jj + 1) & 1][k] = S.digd[jn * m + tid + k * T];
+            else { dl[(jj + 1) & 1][k] = S.diglo[jn * m + tid + k * T]; dh[(jj + 1) & 1][k] = S.dighi[jn * m + tid + k * T]; }
+          }
         }
         if (jj == 2) __syncthreads();                    // previous prime's residue store has left buffers 0,1
         uint32_t x[R0];
+        if constexpr (HF) {
+          head_stage1_f64<R0>(dd[jj & 1], x, fp, fpinv, fw, fwp, fc);
+          fwd_block_tail<LR0>(x, C.topf[i], p, p2, z);
+        } else {
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[jj & 1][k], dh[jj & 1][k], mu, negc, p);
-        fwd_block<LR0>(x, C.topf[i], p, p2, z);
+          for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[jj & 1][k], dh[jj & 1][k], mu, negc, p);
+          fwd_block<LR0>(x, C.topf[i], p, p2, z);
+        }
 #pragma unroll
         for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
       }
@@ -694,7 +642,10 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
     if (i + 1 < L) {                                     // next prime's first digit words: requested before the barrier, so a
 #pragma unroll                                           // warp that arrives early waits with its loads already in flight
-      for (int k = 0; k < R0; ++k) { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+      for (int k = 0; k < R0; ++k) {
+        if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * T];
+        else { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+      }
     }
     __syncthreads();                                     // last reader of `tab` for this prime is done
     {
@@ -723,34 +674,27 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(4);
   }
-  crt_update<LOGM, T, true>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
+  crt_update<LOGM, T, true, HF>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
   if (tid == 0) stage_table(tab, tw_f, m * 8, bar);      // ends with a barrier: the staging area is free again
 #undef SGFHE_TICK
 }
 
-template <int LOGM>
-__global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
-bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
-  extern __shared__ __align__(16) uint32_t sm[];
-  using S4 = Shape4<LOGM>;
+// Persistent gate loop shared by the two gate kernels (V4: fused-pass step for m >= 4096; HF: FP64 head, digits kept as
+// doubles).  SMs do not all run at the same pace (two dies, different distances to L2), so with a work counter a CTA
+// takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
+// F_DECOMP: (re)compute S.dig from S.acc before the first step of this launch (set with F_INIT, and by the
+// trace / external-product seams whose accumulator arrives from a previous launch or from the host).
+template <int LOGM, bool V4, bool HF>
+__device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, uint32_t* sm, uint2* tab, uint64_t* bar,
+                                          uint32_t& parity) {
   constexpr int m = 1 << LOGM;
   const int n = C.n;
-  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
-  uint32_t parity = 0;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    stage_table(tab, A.tw_f, m * 8, bar);
-  }
-  __syncthreads();
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
   const uint64_t rmask = (1ull << C.logr) - 1;
   if (A.stagger_cycles > 0) {                            // experiment knob: CTA b starts (b % slots) * cycles late
     const long long t0 = clock64(), wait = (long long)(blockIdx.x % A.stagger_slots) * A.stagger_cycles;
     while (clock64() - t0 < wait) __nanosleep(256);
   }
-  // Persistent CTAs.  SMs do not all run at the same pace (two dies, different distances to L2), so with a work counter
-  // a CTA takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
   for (int g = blockIdx.x;;) {
     if (A.work_counter) {
       if (threadIdx.x == 0) sm[6 * m + 2] = (uint32_t)atomicAdd(A.work_counter, 1);
@@ -775,16 +719,18 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     __syncthreads();
     const int k_begin = pack ? g : A.step_begin, k_end = pack ? g + 1 : A.step_end;
     if ((A.flags & F_DECOMP) && k_begin < k_end) {
-      decompose_poly<LOGM>(C, S, 0, pack ? nullptr : dr);
-      decompose_poly<LOGM>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
+      decompose_poly<LOGM, HF>(C, S, 0, pack ? nullptr : dr);
+      decompose_poly<LOGM, HF>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
     }
     __syncthreads();
     for (int k = k_begin; k < k_end; ++k) {
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
       const bool more = k + 1 < k_end;
-      gate_step_v4<LOGM>(C, S, sm, A.keyhat + (size_t)k * C.L * 8 * m, A.tw_f,
-                         (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr, u, (A.flags & F_EXT) != 0, more,
-                         tab, bar, parity, blockIdx.x == 0 ? A.timing : nullptr);
+      const uint32_t* keyrow = A.keyhat + (size_t)k * C.L * 8 * m;
+      const int64_t* dn = (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr;
+      unsigned long long* tm = blockIdx.x == 0 ? A.timing : nullptr;
+      if constexpr (V4) gate_step_v4<LOGM, HF>(C, S, sm, keyrow, A.tw_f, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
+      else gate_step<LOGM>(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
     }
     if (A.trace) {
       uint64_t* tr = A.trace + (pack ? (size_t)g * 4 * m : 0);
@@ -801,6 +747,35 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     __syncthreads();
     if (!A.work_counter) g += gridDim.x;
   }
+}
+
+template <int LOGM>
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
+bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  constexpr int m = 1 << LOGM;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);                 // staged twiddle table of the current (prime, direction)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  run_gates<LOGM, false, false>(C, A, sm, tab, bar, parity);
+}
+
+template <int LOGM, bool HF>
+__global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
+bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  constexpr int m = 1 << LOGM;
+  uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage_table(tab, A.tw_f, m * 8, bar);
+  }
+  __syncthreads();
+  run_gates<LOGM, true, HF>(C, A, sm, tab, bar, parity);
   mbar_wait(bar, parity);                                // the table staged for a step that never runs
 }
 
@@ -852,7 +827,7 @@ template <int LOGM>
 __global__ void __launch_bounds__(Shape<LOGM>::T, 1)
 polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
-               uint32_t* scratch, int batch) {
+               uint32_t* scratch, int batch, int b_bcast) {
   extern __shared__ __align__(16) uint32_t sm[];
   using SH = Shape<LOGM>;
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
@@ -875,7 +850,7 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
         ulonglong2 cur[R], nxt[R];
         auto fetch = [&](ulonglong2 (&dst)[R], int e) {
           const int c = e / STR, idx = e % STR;
-          const ulonglong2* src = reinterpret_cast<const ulonglong2*>((c ? b : a) + (size_t)g * m * 2);
+          const ulonglong2* src = reinterpret_cast<const ulonglong2*>(c ? b + (b_bcast ? 0 : (size_t)g * m * 2) : a + (size_t)g * m * 2);
 #pragma unroll
           for (int k = 0; k < R; ++k) dst[k] = src[idx + k * STR];
         };
@@ -933,7 +908,7 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
 template <int LOGM>
 __global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
 polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
-                  uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, uint32_t* scratch, int batch) {
+                  uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, uint32_t* scratch, int batch, int b_bcast) {
   extern __shared__ __align__(16) uint32_t sm[];
   using S4 = Shape4<LOGM>;
   constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, LM = Shape<LOGM>::LM, SB = 6 * LOGM + 8;
@@ -954,7 +929,7 @@ polymul_kernel_v4(const __grid_constant__ DevConst C, const uint64_t* __restrict
     const int g0 = 2 * pr, g1 = (2 * pr + 1 < batch) ? 2 * pr + 1 : g0;     // an odd batch repeats its last product
     // operand polynomial of buffer j: (a, b) of the first product, then of the second
     auto operand = [&](int j) {
-      return reinterpret_cast<const ulonglong2*>(j & 1 ? b : a) + (size_t)(j & 2 ? g1 : g0) * m;
+      return reinterpret_cast<const ulonglong2*>(j & 1 ? b : a) + ((j & 1) && b_bcast ? (size_t)0 : (size_t)(j & 2 ? g1 : g0) * m);
     };
     // Half a polynomial's operand words (8 coefficients per thread, 32 registers) are kept in flight: the second half is
     // requested while the first is reduced, the next polynomial's first half while this one runs its top stages.
@@ -1153,6 +1128,60 @@ __global__ void decrypt_kernel(int n, int count, uint64_t rmask, uint64_t Dr, co
   if (lane == 0) out[w] = (uint8_t)((((l[n] - acc) + Dr / 2) & rmask) / Dr);
 }
 
+// BootstrapKey rows from the products a_j * ext_key (src/fhe.jl:192-198): key[i][j] = (a_j, a_j s + e_j) + s_i G[j,:],
+// G = [1 0; B 0; 0 1; 0 B] (src/fhe.jl:119-122).  a, prod: [rows][4][m][2] wide; e: [rows][4][m]; out: [rows][4][2][m][2].
+__global__ void keygen_assemble_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a,
+                                       const uint64_t* __restrict__ prod, const int64_t* __restrict__ e,
+                                       const uint8_t* __restrict__ sk, int row0, int rows, uint64_t* __restrict__ out) {
+  const int m = C.m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * 4 * m) return;
+  const int k = (int)(idx % m), j = (int)((idx / m) & 3), i = (int)(idx / ((size_t)4 * m));
+  u128 av = (u128)a[2 * idx] | ((u128)a[2 * idx + 1] << 64);
+  u128 bv = (u128)prod[2 * idx] | ((u128)prod[2 * idx + 1] << 64);
+  const int64_t ev = e[idx];
+  bv = ev >= 0 ? addmodQ(bv, (u128)ev, C.Q) : submodQ(bv, (u128)(-ev), C.Q);          // b_j = a_j * s + e_j   (src/fhe.jl:195)
+  if (k == 0 && sk[row0 + i]) {                                                      // + s_i G                 (src/fhe.jl:196)
+    const u128 g = (j & 1) ? C.B : (u128)1;
+    if (j < 2) av = addmodQ(av, g, C.Q); else bv = addmodQ(bv, g, C.Q);
+  }
+  uint64_t* o = out + (((size_t)i * 4 + j) * 2 * m + k) * 2;
+  o[0] = (uint64_t)av; o[1] = (uint64_t)(av >> 64);
+  o[(size_t)2 * m] = (uint64_t)bv; o[(size_t)2 * m + 1] = (uint64_t)(bv >> 64);
+}
+
+// pack_encrypted_bits (src/fhe.jl:675-678): as[i].coeffs[j] = new_lwes[j].a[i] for j < n, 0 above (resize to m)
+__global__ void pack_transpose_kernel(int n, int m, const uint64_t* __restrict__ lwes /* [n][n+1][2] */, uint64_t* __restrict__ polys /* [n][m][2] */) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * m) return;
+  const int j = (int)(idx % m), i = (int)(idx / m);
+  uint64_t lo = 0, hi = 0;
+  if (j < n) { lo = lwes[((size_t)j * (n + 1) + i) * 2]; hi = lwes[((size_t)j * (n + 1) + i) * 2 + 1]; }
+  polys[2 * idx] = lo; polys[2 * idx + 1] = hi;
+}
+
+// pack_encrypted_bits tail (src/fhe.jl:686-693): w~ = sum_i w_i, v~ = sum_i v_i; w = ModRed(-w~), v = ModRed(b - v~) with
+// b.coeffs[j] = new_lwes[j].b for j < n, 0 above.  wv: [n][2][m][2] wide; out_w, out_v: [m] over Z_r.
+__global__ void pack_tail_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ wv,
+                                 const uint64_t* __restrict__ lwes, uint64_t* __restrict__ out_w, uint64_t* __restrict__ out_v) {
+  const int m = C.m, n = C.n;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * m) return;
+  const int c = idx / m, k = idx % m;
+  u128 sum = 0;                                               // n values below Q < 2^93: no overflow
+  for (int i = 0; i < n; ++i) {
+    const uint64_t* t = wv + (((size_t)i * 2 + c) * m + k) * 2;
+    sum += (u128)t[0] | ((u128)t[1] << 64);
+  }
+  sum %= C.Q;
+  if (c == 0) out_w[k] = modred(C, negmodQ(sum, C.Q));
+  else {
+    u128 b = 0;
+    if (k < n) { const uint64_t* t = lwes + ((size_t)k * (n + 1) + n) * 2; b = (u128)t[0] | ((u128)t[1] << 64); }
+    out_v[k] = modred(C, submodQ(b, sum, C.Q));
+  }
+}
+
 // wide [2][m][2] -> accumulator scratch (SoA limbs) and back
 __global__ void acc_load_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ ab, uint32_t* acc) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x, m = C.m;
@@ -1177,6 +1206,7 @@ struct sgfhe_ctx {
   DevConst dc;
   int num_sms = 0, threads = 0, boot_threads = 0, max_ctas = 0;
   bool use_v4 = false;
+  bool head_f64 = true;                            // v4 gate kernel: digits as doubles, first forward stage on the FP64 pipe
   size_t smem_bytes = 0, scratch_stride = 0, zres_stride = 0;
   int persist_l2 = 0;                              // pin accumulator + digit scratch in L2 (access policy window)
   uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
@@ -1185,7 +1215,11 @@ struct sgfhe_ctx {
   uint32_t* d_pm_scratch = nullptr; int pm_ctas = 0;
   uint64_t* d_io = nullptr; size_t io_capacity = 0;
   int* d_counter = nullptr;                        // work counter of the persistent gate kernels
+  uint64_t key_token = 0;                          // identifies the key content of d_keyhat (0 = none); see sgfhe_bkey_token
+  uint8_t* d_arena = nullptr; size_t arena_bytes = 0;   // grow-only staging for the host-buffer entry points
 };
+static std::atomic<uint64_t> g_token{0};
+static void new_key_token(sgfhe_ctx* c) { c->key_token = ++g_token; }
 
 static void to_limbs(u128 v, uint32_t out[3]) { out[0] = (uint32_t)v; out[1] = (uint32_t)(v >> 32); out[2] = (uint32_t)(v >> 64); }
 
@@ -1247,6 +1281,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
     dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p) - 4u * p;      // wraps mod 2^32 on purpose
+    dc->hp_p[i] = (double)p; dc->hp_pinv[i] = 1.0 / (double)p; dc->hp_c[i] = 6755399441055744.0 + 2.0 * (double)p;
   }
   for (int basis = 0; basis < 2; ++basis) {
     const int K = basis == 0 ? L : LM;
@@ -1296,6 +1331,8 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       dc->topf[i][k - 1] = f;
       dc->topi[i][k - 1] = make_uint2((uint32_t)p - mir.x, ~mir.y);
     }
+    dc->hp_w[i] = (double)(*twf)[(size_t)i * m + 1].x;                       // stage-1 twiddle psi^(m/2)
+    dc->hp_wp[i] = dc->hp_w[i] / (double)p;
   }
   return 0;
 }
@@ -1320,12 +1357,14 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
 static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   cudaError_t e = cudaSuccess;
   c->use_v4 = c->hp.logm >= 12 && !getenv("SGFHE_FORCE_V3");
+  c->head_f64 = !getenv("SGFHE_HEAD_INT");           // A/B knob: the all-integer head of round 1
   if (c->use_v4) {
     SGFHE_DISPATCH_V4(c->hp.logm, {
       c->boot_threads = Shape4<LOGM_>::T;
       e = cudaFuncSetAttribute(polymul_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_>, c->boot_threads, c->smem_bytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads, c->smem_bytes);
     });
     if (e != cudaSuccess) return e;
   }
@@ -1354,7 +1393,8 @@ static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, cons
       nattr = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    SGFHE_DISPATCH_V4(c->hp.logm, (cudaLaunchKernelEx(&cfg, bootstrap_kernel_v4<LOGM_>, c->dc, A)));
+    if (c->head_f64) { SGFHE_DISPATCH_V4(c->hp.logm, (cudaLaunchKernelEx(&cfg, bootstrap_kernel_v4<LOGM_, true>, c->dc, A))); }
+    else { SGFHE_DISPATCH_V4(c->hp.logm, (cudaLaunchKernelEx(&cfg, bootstrap_kernel_v4<LOGM_, false>, c->dc, A))); }
   } else {
     SGFHE_DISPATCH(c->hp.logm, (bootstrap_kernel<LOGM_><<<grid, c->threads, c->smem_bytes, st>>>(c->dc, A)));
   }
@@ -1366,15 +1406,15 @@ static void launch_key_transform(const sgfhe_ctx* c, int npolys, const uint64_t*
   ++g_launches;
 }
 static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const uint64_t* a, const uint64_t* b, uint64_t* out,
-                           int batch) {
+                           int batch, int b_bcast = 0) {
   if (c->use_v4 && !getenv("SGFHE_POLYMUL_V3")) {
     SGFHE_DISPATCH_V4(c->hp.logm, (polymul_kernel_v4<LOGM_><<<grid, c->boot_threads, c->smem_bytes, st>>>(
-                                       c->dc, a, b, out, c->d_tw_f, c->d_pm_scratch, batch)));
+                                       c->dc, a, b, out, c->d_tw_f, c->d_pm_scratch, batch, b_bcast)));
     ++g_launches;
     return;
   }
   SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 16 + 16, st>>>(
-                                  c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch)));
+                                  c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch, b_bcast)));
   ++g_launches;
 }
 
@@ -1447,7 +1487,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
 extern "C" int sgfhe_ctx_destroy(sgfhe_ctx* c) {
   if (!c) return SGFHE_OK;
   cudaSetDevice(c->device);
-  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch); cudaFree(c->d_io); cudaFree(c->d_counter);
+  cudaFree(c->d_tw_f); cudaFree(c->d_tw_i); cudaFree(c->d_keyhat); cudaFree(c->d_scratch); cudaFree(c->d_pm_scratch); cudaFree(c->d_io); cudaFree(c->d_counter); cudaFree(c->d_arena);
   delete c;
   return SGFHE_OK;
 }
@@ -1478,6 +1518,16 @@ static int ensure_scratch(sgfhe_ctx* c, int ctas) {
   return SGFHE_OK;
 }
 
+// grow-only device staging shared by the host-buffer entry points (no cudaMalloc / cudaFree per call)
+static int ensure_arena(sgfhe_ctx* c, size_t bytes) {
+  if (bytes <= c->arena_bytes) return SGFHE_OK;
+  cudaFree(c->d_arena); c->d_arena = nullptr; c->arena_bytes = 0;
+  bytes = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  if (cudaMalloc(&c->d_arena, bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of the staging arena failed");
+  c->arena_bytes = bytes;
+  return SGFHE_OK;
+}
+
 // transform `npolys` coefficient-form polys (host) into keyhat starting at poly index poly0
 static int transform_polys(sgfhe_ctx* c, const uint64_t* h_coef, int poly0, int npolys, uint32_t* d_keyhat) {
   const int m = c->hp.m;
@@ -1505,8 +1555,15 @@ extern "C" int sgfhe_bkey_upload(sgfhe_ctx* c, const uint64_t* key, int32_t rows
   if (rows < 1 || rows > c->hp.n) return fail(SGFHE_ERR_ARG, "rows must be in [1, n]");
   CK(cudaSetDevice(c->device));
   int rc = ensure_keyhat(c, rows); if (rc) return rc;
+  c->key_rows = 0; c->key_token = 0;                   // a failed transform leaves no usable key behind
   rc = transform_polys(c, key, 0, rows * 8, c->d_keyhat); if (rc) return rc;
-  c->key_rows = rows;
+  c->key_rows = rows; new_key_token(c);
+  return SGFHE_OK;
+}
+
+extern "C" int sgfhe_bkey_token(const sgfhe_ctx* c, uint64_t* token) {
+  if (!c || !token) return fail(SGFHE_ERR_ARG, "NULL argument");
+  *token = c->key_rows > 0 ? c->key_token : 0;
   return SGFHE_OK;
 }
 
@@ -1516,13 +1573,13 @@ extern "C" int sgfhe_bkey_device_buffer(sgfhe_ctx* c, int32_t rows, void** d_ptr
   CK(cudaSetDevice(c->device));
   int rc = ensure_keyhat(c, rows); if (rc) return rc;
   *d_ptr = c->d_keyhat; *bytes = (uint64_t)rows * keyhat_row_words(c) * sizeof(uint32_t);
-  return SGFHE_OK;
+  return SGFHE_OK;                                     // the caller may read (broadcast root) or overwrite + sgfhe_bkey_adopt
 }
 
 extern "C" int sgfhe_bkey_adopt(sgfhe_ctx* c, int32_t rows) {
   if (!c) return fail(SGFHE_ERR_ARG, "NULL argument");
   if (rows < 1 || (size_t)rows > c->keyhat_capacity_rows) return fail(SGFHE_ERR_ARG, "rows exceeds the key buffer");
-  c->key_rows = rows;
+  c->key_rows = rows; new_key_token(c);
   return SGFHE_OK;
 }
 
@@ -1564,8 +1621,9 @@ extern "C" int sgfhe_bkey_import(sgfhe_ctx* c, const void* blob, uint64_t bytes)
   if (bytes < need) return fail(SGFHE_ERR_ARG, "truncated blob");
   CK(cudaSetDevice(c->device));
   int rc = ensure_keyhat(c, h.rows); if (rc) return rc;
+  c->key_rows = 0; c->key_token = 0;
   CK(cudaMemcpy(c->d_keyhat, static_cast<const char*>(blob) + sizeof h, need - sizeof h, cudaMemcpyHostToDevice));
-  c->key_rows = h.rows;
+  c->key_rows = h.rows; new_key_token(c);
   return SGFHE_OK;
 }
 
@@ -1646,6 +1704,25 @@ extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t
 }
 
 
+// _bootstrap_internal for a batch with device buffers: out_* [batch][n+1][2] wide over Z_Q
+static int internal_batch_device(sgfhe_ctx* c, int batch, const uint64_t* d_l1, const uint64_t* d_l2, const int64_t* d_draws,
+                                 uint64_t* d_and, uint64_t* d_or, uint64_t* d_xor, cudaStream_t st) {
+  GateArgs A; memset(&A, 0, sizeof A);
+  A.lwe1 = d_l1; A.lwe2 = d_l2; A.draws = d_draws; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor;
+  A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL | F_RAW;
+  return launch_gates(c, A, st);
+}
+
+// shortened_external_product batch with device buffers: d_polys [count][m][2], d_out [count][2][m][2]
+static int shortened_device(sgfhe_ctx* c, int count, const uint64_t* d_polys, const int64_t* d_draws, uint64_t* d_out,
+                            uint64_t* d_dummy, cudaStream_t st) {
+  GateArgs A; memset(&A, 0, sizeof A);
+  A.lwe1 = d_dummy; A.lwe2 = d_dummy; A.out_and = A.out_or = A.out_xor = d_dummy;
+  A.batch = count; A.flags = F_EXT | F_DECOMP | F_PACK;
+  A.pack_in = d_polys; A.pack_draws = d_draws; A.trace = d_out;
+  return launch_gates(c, A, st);
+}
+
 extern "C" int sgfhe_bootstrap_internal_batch(sgfhe_ctx* c, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,
                                               const int64_t* draws, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor) {
   if (!c || !lwe1 || !lwe2 || !out_and || !out_or || !out_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
@@ -1655,25 +1732,18 @@ extern "C" int sgfhe_bootstrap_internal_batch(sgfhe_ctx* c, int32_t batch, const
   CK(cudaSetDevice(c->device));
   const size_t lwe_w = (size_t)batch * (c->hp.n + 1);
   const size_t draw_bytes = draws ? (size_t)batch * c->hp.n * 4 * c->hp.m * sizeof(int64_t) : 0;
-  uint64_t* d_io = nullptr; int64_t* d_draws = nullptr;
-  if (cudaMalloc(&d_io, (2 + 6) * lwe_w * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of LWE buffers failed");
-  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) { cudaFree(d_io); return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed"); }
-  int rc = SGFHE_OK;
-  cudaError_t e = cudaMemcpy(d_io, lwe1, lwe_w * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_io + lwe_w, lwe2, lwe_w * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    GateArgs A; memset(&A, 0, sizeof A);
-    A.lwe1 = d_io; A.lwe2 = d_io + lwe_w; A.draws = d_draws;
-    A.out_and = d_io + 2 * lwe_w; A.out_or = d_io + 4 * lwe_w; A.out_xor = d_io + 6 * lwe_w;
-    A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL | F_RAW;
-    rc = launch_gates(c, A, nullptr);
-    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
-  }
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_and, d_io + 2 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_or, d_io + 4 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out_xor, d_io + 6 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost);
-  cudaFree(d_io); cudaFree(d_draws);
+  int rc = ensure_arena(c, 8 * lwe_w * 8 + draw_bytes); if (rc) return rc;
+  uint64_t* d_io = reinterpret_cast<uint64_t*>(c->d_arena);
+  int64_t* d_draws = draws ? reinterpret_cast<int64_t*>(c->d_arena + 8 * lwe_w * 8) : nullptr;
+  cudaError_t e = cudaMemcpyAsync(d_io, lwe1, lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_io + lwe_w, lwe2, lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws) e = cudaMemcpyAsync(d_draws, draws, draw_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = internal_batch_device(c, batch, d_io, d_io + lwe_w, d_draws, d_io + 2 * lwe_w, d_io + 4 * lwe_w, d_io + 6 * lwe_w, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_and, d_io + 2 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_or, d_io + 4 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_xor, d_io + 6 * lwe_w, lwe_w * 16, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_internal_batch: ") + cudaGetErrorString(e));
   return SGFHE_OK;
@@ -1686,25 +1756,128 @@ extern "C" int sgfhe_shortened_products(sgfhe_ctx* c, int32_t count, const uint6
   if (count == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
   const size_t m = c->hp.m, in_w = (size_t)count * m * 2, out_w = (size_t)count * 4 * m;
-  uint64_t* d = nullptr; int64_t* d_draws = nullptr;
-  if (cudaMalloc(&d, (in_w + out_w + 8) * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
-  if (draws && cudaMalloc(&d_draws, in_w * 8) != cudaSuccess) { cudaFree(d); return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed"); }
-  int rc = SGFHE_OK;
-  cudaError_t e = cudaMemcpy(d, polys, in_w * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && draws) e = cudaMemcpy(d_draws, draws, in_w * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) {
-    GateArgs A; memset(&A, 0, sizeof A);
-    uint64_t* dummy = d + in_w + out_w;
-    A.lwe1 = dummy; A.lwe2 = dummy; A.out_and = A.out_or = A.out_xor = dummy;
-    A.batch = count; A.flags = F_EXT | F_DECOMP | F_PACK;
-    A.pack_in = d; A.pack_draws = d_draws; A.trace = d + in_w;
-    rc = launch_gates(c, A, nullptr);
-    if (rc == SGFHE_OK) e = cudaDeviceSynchronize();
-  }
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpy(out, d + in_w, out_w * 8, cudaMemcpyDeviceToHost);
-  cudaFree(d); cudaFree(d_draws);
+  int rc = ensure_arena(c, (in_w + out_w + 8 + (draws ? in_w : 0)) * 8); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
+  int64_t* d_draws = draws ? reinterpret_cast<int64_t*>(d + in_w + out_w + 8) : nullptr;
+  cudaError_t e = cudaMemcpyAsync(d, polys, in_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws) e = cudaMemcpyAsync(d_draws, draws, in_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = shortened_device(c, count, d, d_draws, d + in_w, d + in_w + out_w, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d + in_w, out_w * 8, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("shortened_products: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+// pack_encrypted_bits(bkey, rng|nothing, enc_bits) (src/fhe.jl:660-696), every stage on the device:
+//   n internal bootstraps of (trivial(1), bit_i) keeping the AND output over Z_Q (:670-673), transposition into n polynomials
+//   of length m (:675-678), n shortened external products against key rows i (:683-684), the two sums, negate / subtract
+//   (:686-690) and ModRed to r (:692-693).
+extern "C" int sgfhe_pack_encrypted_bits(sgfhe_ctx* c, const uint64_t* enc_bits, const int64_t* draws_boot,
+                                         const int64_t* draws_short, uint64_t* out_w, uint64_t* out_v) {
+  if (!c || !enc_bits || !out_w || !out_v) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  CK(cudaSetDevice(c->device));
+  const size_t n = c->hp.n, m = c->hp.m, lwe_w = n * (n + 1);
+  const size_t db_bytes = draws_boot ? n * n * 4 * m * 8 : 0, ds_bytes = draws_short ? n * m * 2 * 8 : 0;
+  // layout (uint64 words): triv | bits | and, or, xor (wide) | polys | wv | w, v | dummy | draws
+  const size_t o_triv = 0, o_bits = lwe_w, o_and = 2 * lwe_w, o_or = 4 * lwe_w, o_xor = 6 * lwe_w, o_polys = 8 * lwe_w,
+               o_wv = o_polys + n * m * 2, o_w = o_wv + n * 4 * m, o_v = o_w + m, o_dummy = o_v + m, o_db = o_dummy + 8,
+               o_ds = o_db + db_bytes / 8, total = o_ds + ds_bytes / 8;
+  int rc = ensure_arena(c, total * 8); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
+  std::vector<uint64_t> triv(lwe_w, 0);
+  for (size_t i = 0; i < n; ++i) triv[i * (n + 1) + n] = c->hp.Dr;       // trivial LWE encrypting 1 (src/fhe.jl:670-671)
+  cudaError_t e = cudaMemcpyAsync(d + o_triv, triv.data(), lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_bits, enc_bits, lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws_boot) e = cudaMemcpyAsync(d + o_db, draws_boot, db_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws_short) e = cudaMemcpyAsync(d + o_ds, draws_short, ds_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);                // `triv` leaves scope-safe
+  if (e == cudaSuccess) rc = internal_batch_device(c, (int)n, d + o_triv, d + o_bits, draws_boot ? reinterpret_cast<int64_t*>(d + o_db) : nullptr,
+                                                   d + o_and, d + o_or, d + o_xor, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) {
+    pack_transpose_kernel<<<(unsigned)((n * m + 255) / 256), 256>>>((int)n, (int)m, d + o_and, d + o_polys);
+    ++g_launches;
+    e = cudaGetLastError();
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess)
+    rc = shortened_device(c, (int)n, d + o_polys, draws_short ? reinterpret_cast<int64_t*>(d + o_ds) : nullptr, d + o_wv, d + o_dummy, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) {
+    pack_tail_kernel<<<(unsigned)((2 * m + 127) / 128), 128>>>(c->dc, d + o_wv, d + o_and, d + o_w, d + o_v);
+    ++g_launches;
+    e = cudaGetLastError();
+  }
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_w, d + o_w, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_v, d + o_v, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("pack_encrypted_bits: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+// BootstrapKey(rng, sk) (src/fhe.jl:181-201) on the device, output already in the transform domain.
+//   sk: n bytes (0/1).  a_rand: [rows][4][m][2] wide, the uniform polynomials a_1..a_4 of rows row0.. (src/fhe.jl:193);
+//   e_rand: [rows][4][m] int64 in [-n, n] (src/fhe.jl:194) -- the caller's RNG draws them in the reference's order.
+//   The 4 rows products a_j * ext_key (src/fhe.jl:195), + e_j, + s_i G (src/fhe.jl:196) and the key pre-transform run on the
+//   device; key_out (NULL or host [rows][4][2][m][2] wide) receives the coefficient form only on request.
+extern "C" int sgfhe_bkey_generate(sgfhe_ctx* c, const uint8_t* sk, const uint64_t* a_rand, const int64_t* e_rand,
+                                   int32_t row0, int32_t rows, uint64_t* key_out) {
+  if (!c || !sk || !a_rand || !e_rand) return fail(SGFHE_ERR_ARG, "NULL argument");
+  const int n = c->hp.n; const size_t m = c->hp.m;
+  if (row0 < 0 || rows < 1 || row0 + rows > n) return fail(SGFHE_ERR_ARG, "rows out of range");
+  if (row0 > c->key_rows) return fail(SGFHE_ERR_STATE, "key rows must be generated in order (row0 exceeds the rows present)");
+  CK(cudaSetDevice(c->device));
+  int rc = SGFHE_OK;
+  if ((size_t)n > c->keyhat_capacity_rows) {           // growing the buffer drops its content: only legal at the start
+    if (row0 != 0) return fail(SGFHE_ERR_STATE, "key buffer smaller than n rows: start at row 0");
+    rc = ensure_keyhat(c, n); if (rc) return rc;
+  }
+  const int chunk = (int)std::max<size_t>(1, ((size_t)1 << 25) / (4 * m * 16) * 4);    // rows per pass: <= 128 MiB of a_rand
+  // arena: sk | ext (m wide) | a | prod | e | coef
+  const size_t crow = (size_t)(rows < chunk ? rows : chunk);
+  const size_t o_sk = 0, o_ext = 1024, o_a = o_ext + m * 16, o_prod = o_a + crow * 4 * m * 16, o_e = o_prod + crow * 4 * m * 16,
+               o_coef = o_e + crow * 4 * m * 8, total = o_coef + crow * 8 * m * 16;
+  if (n > 1024) return fail(SGFHE_ERR_ARG, "n too large");
+  rc = ensure_arena(c, total); if (rc) return rc;
+  uint8_t* d = c->d_arena;
+  std::vector<uint64_t> ext(m * 2, 0);
+  for (int i = 0; i < n; ++i) ext[2 * (size_t)i] = sk[i] ? 1 : 0;           // resize(polynomial_Q(sk.key), m)  (src/fhe.jl:185)
+  CK(cudaMemcpy(d + o_sk, sk, n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d + o_ext, ext.data(), m * 16, cudaMemcpyHostToDevice));
+  const int old_rows = c->key_rows;
+  c->key_rows = row0 < old_rows ? row0 : old_rows; c->key_token = 0;        // rows from row0 on are being rewritten
+  for (int done = 0; done < rows; done += (int)crow) {
+    const int cnt = rows - done < (int)crow ? rows - done : (int)crow;
+    const size_t polys = (size_t)cnt * 4;
+    CK(cudaMemcpyAsync(d + o_a, a_rand + (size_t)done * 4 * m * 2, polys * m * 16, cudaMemcpyHostToDevice, nullptr));
+    CK(cudaMemcpyAsync(d + o_e, e_rand + (size_t)done * 4 * m, polys * m * 8, cudaMemcpyHostToDevice, nullptr));
+    {                                                   // products a_j * ext_key, second operand broadcast
+      const bool v4 = c->use_v4 && !getenv("SGFHE_POLYMUL_V3");
+      const int cap = v4 ? c->num_sms : c->num_sms * 2, units = v4 ? ((int)polys + 1) / 2 : (int)polys;
+      const int grid = units < cap ? units : cap;
+      if (grid > c->pm_ctas) {
+        cudaFree(c->d_pm_scratch); c->d_pm_scratch = nullptr; c->pm_ctas = 0;
+        if (cudaMalloc(&c->d_pm_scratch, (size_t)grid * c->dc.LM * 2 * m * sizeof(uint32_t)) != cudaSuccess)
+          return fail(SGFHE_ERR_NOMEM, "cudaMalloc of polymul scratch failed");
+        c->pm_ctas = grid;
+      }
+      launch_polymul(c, grid, nullptr, reinterpret_cast<uint64_t*>(d + o_a), reinterpret_cast<uint64_t*>(d + o_ext),
+                     reinterpret_cast<uint64_t*>(d + o_prod), (int)polys, 1);
+      CK(cudaGetLastError());
+    }
+    keygen_assemble_kernel<<<(unsigned)((polys * m + 255) / 256), 256>>>(c->dc, reinterpret_cast<uint64_t*>(d + o_a),
+        reinterpret_cast<uint64_t*>(d + o_prod), reinterpret_cast<int64_t*>(d + o_e), d + o_sk, row0 + done, cnt,
+        reinterpret_cast<uint64_t*>(d + o_coef));
+    ++g_launches;
+    CK(cudaGetLastError());
+    launch_key_transform(c, cnt * 8, reinterpret_cast<uint64_t*>(d + o_coef), c->d_keyhat, (row0 + done) * 8);
+    CK(cudaGetLastError());
+    if (key_out) CK(cudaMemcpyAsync(key_out + (size_t)done * 8 * m * 2, d + o_coef, (size_t)cnt * 8 * m * 16, cudaMemcpyDeviceToHost, nullptr));
+    CK(cudaDeviceSynchronize());
+  }
+  c->key_rows = std::max(old_rows, row0 + rows); new_key_token(c);
   return SGFHE_OK;
 }
 
