@@ -370,14 +370,10 @@ def run_depth(args) -> None:
     n, W, layers = args.n, args.batch, args.layers
     P = sg.Params(n, device=local)
     sk = sg.PrivateKey(P, np.random.default_rng([args.seed, 1]))
-    if rank == 0:
-        bkey = sg.BootstrapKey(np.random.default_rng([args.seed, 2]), sk)
-        bkey.upload()
-    else:
-        bkey = sg.BootstrapKey(params=P, key=np.zeros((0, 4, 2, P.m, 2), np.uint64))
-        bkey._uploaded = True
+    bkey = sg.BootstrapKey(np.random.default_rng([args.seed, 2]), sk) if rank == 0 else None   # generated on the device
     if world > 1:
         sg.broadcast_key(P, n, dist)
+        bkey = sg.BootstrapKey.resident(P)
     rng = np.random.default_rng([args.seed, 3, rank])
     bits, lw = [], []
     for _ in range((2 * W + n - 1) // n):

@@ -72,6 +72,21 @@ const char* sgfhe_last_error(void);
  * rows == n for a usable key; rows < n is accepted for truncated traces only. */
 int sgfhe_bkey_upload(sgfhe_ctx* ctx, const uint64_t* key, int32_t rows);
 
+/* BootstrapKey(rng, sk) (src/fhe.jl:181-201) on the device, leaving the key in the context already pre-transformed.
+ * sk: n bytes (0/1).  a_rand: host [rows][4][m][2] wide, the uniform polynomials a_1..a_4 of key rows row0..row0+rows-1
+ * (src/fhe.jl:193); e_rand: host int64 [rows][4][m], the errors in [-n, n] (src/fhe.jl:194) -- both drawn by the caller's
+ * RNG in the reference's order (per row: a_1..a_4, then e_1..e_4).  The products a_j * ext_key, + e_j (src/fhe.jl:195),
+ * + s_i G (src/fhe.jl:196) and the pre-transform run on the device.  Rows must be generated in order (row0 <= rows
+ * present); key_out: NULL, or host [rows][4][2][m][2] wide receiving the coefficient form (= bkey.key) on request. */
+int sgfhe_bkey_generate(sgfhe_ctx* ctx, const uint8_t* sk, const uint64_t* a_rand, const int64_t* e_rand,
+                        int32_t row0, int32_t rows, uint64_t* key_out);
+
+/* A context holds ONE key.  Every call that changes it (upload, generate, import, adopt) gives it a new non-zero token;
+ * a host-side key object remembers the token it obtained and compares before use, so that a second key uploaded to the
+ * same context is noticed instead of silently used (the reference's bootstrap is a pure function of bkey).
+ * token = 0: no key.  rows (may be NULL): key rows present. */
+int sgfhe_bkey_token(const sgfhe_ctx* ctx, uint64_t* token, int32_t* rows);
+
 /* bootstrap(bkey, rng|nothing, enc_bit1, enc_bit2) for a batch of independent gates
  * (src/fhe.jl:608-621 -> _bootstrap_internal src/fhe.jl:559-595 -> reduce_modulus src/fhe.jl:644-648).
  * lwe1, lwe2: host [batch][n+1] over Z_r.  out_*: host [batch][n+1] over Z_r.
@@ -108,6 +123,20 @@ int sgfhe_bootstrap_internal_batch(sgfhe_ctx* ctx, int32_t batch, const uint64_t
  * polys: host [count][m][2] wide; draws: NULL or [count][m][2]; out: [count][2][m][2] wide (w_i then v_i). */
 int sgfhe_shortened_products(sgfhe_ctx* ctx, int32_t count, const uint64_t* polys, const int64_t* draws,
                              uint64_t* out);
+
+/* pack_encrypted_bits(bkey, rng|nothing, enc_bits) (src/fhe.jl:660-696), every stage on the device: n internal
+ * bootstraps of (trivial(1), enc_bits[i]) keeping the AND output over Z_Q (:670-673), the transposition (:675-678), n
+ * shortened external products (:683-684), the sums over i, negate / subtract (:686-690) and ModRed Q -> r (:692-693).
+ * enc_bits: host [n][n+1] over Z_r.  draws_boot: NULL or int64 [n][n][2][m][2] (the n bootstraps, in call order);
+ * draws_short: NULL or int64 [n][m][2] (the n shortened products) -- both NULL or both given, as one rng serves both.
+ * out_w, out_v: host [m] over Z_r = the RLWE ciphertext Ciphertext(params, w, v) (src/fhe.jl:695). */
+int sgfhe_pack_encrypted_bits(sgfhe_ctx* ctx, const uint64_t* enc_bits, const int64_t* draws_boot,
+                              const int64_t* draws_short, uint64_t* out_w, uint64_t* out_v);
+
+/* Test seam: the stages of pack_encrypted_bits AFTER the n bootstraps (src/fhe.jl:675-693) from given LWEs over Z_Q.
+ * new_lwes: host [n][n+1][2] wide; draws_short: NULL or int64 [n][m][2]; out_w, out_v: host [m] over Z_r. */
+int sgfhe_pack_from_lwes(sgfhe_ctx* ctx, const uint64_t* new_lwes, const int64_t* draws_short, uint64_t* out_w,
+                         uint64_t* out_v);
 
 /* Negacyclic products in Z_Q[x]/(x^m+1): out[i] = a[i] * b[i], DarkIntegers `Polynomial *` as called at
  * src/fhe.jl:195,527-528.  a, b, out: host [batch][m][2] wide canonical. */

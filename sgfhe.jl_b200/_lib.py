@@ -23,6 +23,7 @@ SYMBOLS = [
     "sgfhe_scheme2_params_derive", "sgfhe_rns2_op", "sgfhe_rns2_op_device",
     "sgfhe_bkey_export_size", "sgfhe_bkey_export", "sgfhe_bkey_import",
     "sgfhe_split_ciphertext", "sgfhe_split_ciphertext_device", "sgfhe_decrypt_bits", "sgfhe_decrypt_bits_device",
+    "sgfhe_bkey_generate", "sgfhe_bkey_token", "sgfhe_pack_encrypted_bits", "sgfhe_pack_from_lwes",
 ]
 
 
@@ -76,6 +77,10 @@ def lib():
         L.sgfhe_split_ciphertext_device.argtypes = [vp, i32, i32, u64p, u64p, u64p, vp]
         L.sgfhe_decrypt_bits.argtypes = [vp, i32, u64p, vp, vp]
         L.sgfhe_decrypt_bits_device.argtypes = [vp, i32, u64p, vp, vp, vp]
+        L.sgfhe_bkey_generate.argtypes = [vp, vp, u64p, vp, i32, i32, u64p]
+        L.sgfhe_bkey_token.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        L.sgfhe_pack_encrypted_bits.argtypes = [vp, u64p, vp, vp, u64p, u64p]
+        L.sgfhe_pack_from_lwes.argtypes = [vp, u64p, vp, u64p, u64p]
         L.sgfhe_scheme2_params_derive.argtypes = [i32, C.POINTER(Scheme2ParamsC)]
         L.sgfhe_rns2_op.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p]
         L.sgfhe_rns2_op_device.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, vp]

@@ -195,25 +195,6 @@ def decrypt(key: PrivateKey, ct):
     return v.astype(bool)
 
 
-def _wide_add_small(w: np.ndarray, e: np.ndarray, Q: int) -> np.ndarray:
-    """(w + e) mod Q for wide w in [0,Q) (uint64[...,2]) and small signed e (|e| < 2^62)."""
-    lo, hi = w[..., 0], w[..., 1]
-    eu = e.astype(np.int64).view(np.uint64)
-    with np.errstate(over="ignore"):
-        lo2 = lo + eu
-        carry = ((e >= 0) & (lo2 < lo)).astype(np.uint64)
-        borrow = ((e < 0) & (lo2 > lo)).astype(np.uint64)
-        hi2 = hi + carry - borrow
-        qlo, qhi = np.uint64(Q & 0xFFFFFFFFFFFFFFFF), np.uint64(Q >> 64)
-        neg = (hi2 >> np.uint64(63)) != 0                       # went below zero: add Q
-        ge = ~neg & ((hi2 > qhi) | ((hi2 == qhi) & (lo2 >= qlo)))   # >= Q: subtract Q
-        lo3 = np.where(neg, lo2 + qlo, np.where(ge, lo2 - qlo, lo2))
-        c_add = (neg & (lo3 < lo2)).astype(np.uint64)
-        b_sub = (ge & (lo2 < qlo)).astype(np.uint64)
-        hi3 = np.where(neg, hi2 + qhi + c_add, np.where(ge, hi2 - qhi - b_sub, hi2))
-    return np.stack([lo3, hi3], axis=-1)
-
-
 def _rand_below(rng: np.random.Generator, bound: int, shape) -> np.ndarray:
     """uniform on [0, bound) as wide uint64[..., 2] (rejection sampling)"""
     bits = bound.bit_length()
@@ -234,56 +215,70 @@ def _rand_below(rng: np.random.Generator, bound: int, shape) -> np.ndarray:
 
 
 class BootstrapKey:
-    """BootstrapKey(rng, sk) -- src/fhe.jl:176-203.
+    """BootstrapKey(rng, sk) -- src/fhe.jl:176-203, generated on the device.
 
     Per row i the draws are a_1..a_4 (uniform on [0,Q), m each) then e_1..e_4 (uniform on [-n,n]) as at
-    src/fhe.jl:193-194; the 4n products a_j * ext_key (src/fhe.jl:195) run on the GPU through
-    sgfhe_polymul.  `key` (uint64[n,4,2,m,2], canonical wide residues) is kept on the host in the
-    reference's layout and uploaded/pre-transformed once."""
+    src/fhe.jl:193-194, made by the caller's rng on the host; the 4n products a_j * ext_key, + e_j (src/fhe.jl:195),
+    + s_i G (src/fhe.jl:196) and the pre-transform run in libsgfhe_cuda.so (sgfhe_bkey_generate), which leaves the key
+    in the context in transform-domain form.  `key` (uint64[n,4,2,m,2], canonical wide residues, the reference's
+    bkey.key[i][j,c].coeffs[k]) is kept on the host only with keep_coefficients=True or when an existing array is adopted
+    with BootstrapKey(params=P, key=array).
+
+    A Params context holds one key at a time; every key object remembers the token of its device copy and re-uploads
+    (or, with no coefficient form to upload from, raises) when another key has replaced it."""
 
     def __init__(self, rng: np.random.Generator | None = None, sk: PrivateKey | None = None, *,
-                 params: Params | None = None, key: np.ndarray | None = None, rows: int | None = None):
+                 params: Params | None = None, key: np.ndarray | None = None, rows: int | None = None,
+                 keep_coefficients: bool = False):
+        self._token = 0
         if key is not None:                       # adopt an existing key[i][j,c] array
             self.params = params
             self.key = np.ascontiguousarray(key, np.uint64)
-        else:
-            P = sk.params
-            self.params = P
-            ext = np.zeros((P.m, 2), np.uint64)
-            ext[: P.n, 0] = sk.key                                                   # src/fhe.jl:185
-            nrows = P.n if rows is None else rows
-            self.key = np.zeros((nrows, 4, 2, P.m, 2), np.uint64)
-            chunk = max(1, min(nrows, (1 << 22) // (4 * P.m)))
-            for i0 in range(0, nrows, chunk):
-                i1 = min(nrows, i0 + chunk)
-                aj = np.zeros((i1 - i0, 4, P.m, 2), np.uint64)
-                ej = np.zeros((i1 - i0, 4, P.m), np.int64)
-                for i in range(i0, i1):
-                    aj[i - i0] = _rand_below(rng, P.Q, (4, P.m))                     # src/fhe.jl:193
-                    ej[i - i0] = rng.integers(-P.n, P.n + 1, size=(4, P.m), dtype=np.int64)   # src/fhe.jl:194
-                prod = polymul(P, aj.reshape(-1, P.m, 2), np.broadcast_to(ext, ((i1 - i0) * 4, P.m, 2)))
-                bj = _wide_add_small(prod.reshape(i1 - i0, 4, P.m, 2), ej, P.Q)       # src/fhe.jl:195
-                self.key[i0:i1, :, 0] = aj
-                self.key[i0:i1, :, 1] = bj
-                for i in range(i0, i1):                                              # + s_i G  src/fhe.jl:196, 119-122
-                    if sk.key[i]:
-                        g = np.array([1, P.B, 1, P.B], dtype=object)
-                        for j in range(4):
-                            c = 0 if j < 2 else 1
-                            cell = self.key[i, j, c, 0]
-                            v = (_wide_to_int(cell) + int(g[j])) % P.Q
-                            cell[0], cell[1] = v & 0xFFFFFFFFFFFFFFFF, v >> 64
-        self._uploaded = False
+            self.rows = self.key.shape[0]
+            return
+        if sk is None:                            # device-resident key placed by import / broadcast: see resident()
+            self.params, self.key, self.rows = params, None, 0
+            return
+        P = sk.params
+        self.params = P
+        nrows = P.n if rows is None else rows
+        self.rows = nrows
+        self.key = np.zeros((nrows, 4, 2, P.m, 2), np.uint64) if keep_coefficients else None
+        skb = np.ascontiguousarray(sk.key, np.uint8)
+        chunk = max(1, min(nrows, (1 << 22) // (4 * P.m)))
+        L = _lib.lib()
+        for i0 in range(0, nrows, chunk):
+            i1 = min(nrows, i0 + chunk)
+            aj = np.zeros((i1 - i0, 4, P.m, 2), np.uint64)
+            ej = np.zeros((i1 - i0, 4, P.m), np.int64)
+            for i in range(i0, i1):
+                aj[i - i0] = _rand_below(rng, P.Q, (4, P.m))                     # src/fhe.jl:193
+                ej[i - i0] = rng.integers(-P.n, P.n + 1, size=(4, P.m), dtype=np.int64)   # src/fhe.jl:194
+            out = self.key[i0:i1] if keep_coefficients else None
+            check(L.sgfhe_bkey_generate(P.ctx, _ptr(skb), _ptr(aj), _ptr(ej), i0, i1 - i0, _ptr(out)))
+        self._token = _ctx_key_state(P)[0]
+
+    @classmethod
+    def resident(cls, params: "Params") -> "BootstrapKey":
+        """The key currently in the context (after BootstrapKey.load_transformed or parallel.broadcast_key)."""
+        bk = cls(params=params)
+        bk._token, bk.rows = _ctx_key_state(params)
+        if not bk._token:
+            raise SgfheError("no bootstrap key in this context")
+        return bk
+
+    def rebind(self):
+        """Adopt the context's current key as this object's device copy (the root rank after broadcast_key)."""
+        self._token = _ctx_key_state(self.params)[0]
 
     def save_transformed(self, path: str):
         """Write the pre-transformed (device) key to `path`; reload with BootstrapKey.load_transformed."""
         self.upload()
         L = _lib.lib()
-        rows = self.key.shape[0] if self.key is not None else self.params.n
         nbytes = C.c_uint64()
-        check(L.sgfhe_bkey_export_size(self.params.ctx, rows, C.byref(nbytes)))
+        check(L.sgfhe_bkey_export_size(self.params.ctx, self.rows, C.byref(nbytes)))
         buf = np.empty(nbytes.value, np.uint8)
-        check(L.sgfhe_bkey_export(self.params.ctx, rows, _ptr(buf), nbytes.value))
+        check(L.sgfhe_bkey_export(self.params.ctx, self.rows, _ptr(buf), nbytes.value))
         buf.tofile(path)
 
     @classmethod
@@ -291,14 +286,24 @@ class BootstrapKey:
         """A key usable for bootstrap straight from a file written by save_transformed (no coefficient form kept)."""
         buf = np.fromfile(path, np.uint8)
         check(_lib.lib().sgfhe_bkey_import(params.ctx, _ptr(buf), buf.size))
-        bk = cls(params=params, key=np.zeros((0, 4, 2, params.m, 2), np.uint64))
-        bk._uploaded = True
-        return bk
+        return cls.resident(params)
 
     def upload(self):
-        if not self._uploaded:
-            check(_lib.lib().sgfhe_bkey_upload(self.params.ctx, _ptr(self.key), self.key.shape[0]))
-            self._uploaded = True
+        """Make sure the context holds THIS key (src/fhe.jl:608: bootstrap is a pure function of bkey)."""
+        tok, _ = _ctx_key_state(self.params)
+        if self._token and tok == self._token:
+            return
+        if self.key is None:
+            raise SgfheError("this key's device copy was replaced by another key on the same Params and no coefficient "
+                             "form was kept (keep_coefficients=True) to upload it again")
+        check(_lib.lib().sgfhe_bkey_upload(self.params.ctx, _ptr(self.key), self.key.shape[0]))
+        self._token = _ctx_key_state(self.params)[0]
+
+
+def _ctx_key_state(P: Params) -> tuple[int, int]:
+    tok, rows = C.c_uint64(), C.c_int32()
+    check(_lib.lib().sgfhe_bkey_token(P.ctx, C.byref(tok), C.byref(rows)))
+    return tok.value, rows.value
 
 
 def _draws(P: Params, rng: np.random.Generator, shape) -> np.ndarray:
@@ -328,53 +333,22 @@ def bootstrap(bkey: BootstrapKey, rng, enc_bit1: EncryptedBit, enc_bit2: Encrypt
     return tuple(EncryptedBit(LWE(o[0, :-1], o[0, -1])) for o in outs)
 
 
-def _wide_sum_mod(w: np.ndarray, Q: int) -> list[int]:
-    """sum over axis 0 of wide values uint64[k, ..., 2] -> flat list of Python ints mod Q (32-bit limb sums, no overflow)"""
-    limbs = np.stack([w[..., 0] & np.uint64(0xFFFFFFFF), w[..., 0] >> np.uint64(32),
-                      w[..., 1] & np.uint64(0xFFFFFFFF), w[..., 1] >> np.uint64(32)], axis=-1)
-    tot = limbs.sum(axis=0, dtype=np.uint64).reshape(-1, 4)
-    return [(int(t[0]) + (int(t[1]) << 32) + (int(t[2]) << 64) + (int(t[3]) << 96)) % Q for t in tot]
-
-
-def _rescale_round(x: int, new_max: int, old_max: int) -> int:
-    """rescale(new_max, x, old_max, round=true) -- src/utils.jl:78-92 (host copy for the m output coefficients of packing)"""
-    q, rem = divmod(x * new_max, old_max)
-    if rem >= old_max // 2 + (old_max & 1):
-        q += 1
-        if q == new_max:
-            q = 0
-    return q
-
-
 def pack_encrypted_bits(bkey: BootstrapKey, rng, enc_bits) -> Ciphertext:
-    """pack_encrypted_bits(bkey, rng|nothing, enc_bits) -- src/fhe.jl:660-696.
-
-    The n internal bootstraps (src/fhe.jl:673) and the n shortened external products (src/fhe.jl:683-684) run on the
-    GPU; the transposition, the two sums over i and the final ModRed of 2m coefficients are host work."""
+    """pack_encrypted_bits(bkey, rng|nothing, enc_bits) -- src/fhe.jl:660-696, every stage on the device
+    (sgfhe_pack_encrypted_bits): the n internal bootstraps (src/fhe.jl:673), the transposition (:675-678), the n
+    shortened external products (:683-684), the two sums, negate / subtract (:686-690) and the final ModRed (:692-693).
+    With an rng the draws are made here in the reference's order: the n bootstraps first, then the n products."""
     P = bkey.params
     if len(enc_bits) != P.n:
         raise SgfheError("expected n encrypted bits (src/fhe.jl:667)")
     bkey.upload()
-    L = _lib.lib()
     n, m = P.n, P.m
-    triv = np.zeros((n, n + 1), np.uint64)
-    triv[:, n] = P.Dr                                                     # trivial LWE encrypting 1, src/fhe.jl:670-671
     bits = np.ascontiguousarray(np.stack([e.lwe.flat() for e in enc_bits]), np.uint64)
     draws = None if rng is None else _draws(P, rng, (n, n, 2, m, 2))
-    outs = [np.zeros((n, n + 1, 2), np.uint64) for _ in range(3)]
-    check(L.sgfhe_bootstrap_internal_batch(P.ctx, n, _ptr(triv), _ptr(bits), _ptr(draws), *[_ptr(o) for o in outs]))
-    new_lwes = outs[0]                                                    # [1] = AND output, before ModRed (src/fhe.jl:673)
-    polys = np.zeros((n, m, 2), np.uint64)
-    polys[:, :n, :] = np.transpose(new_lwes[:, :n, :], (1, 0, 2))         # as[i][j] = new_lwes[j].a[i], resized to m (:675-677)
     ds = None if rng is None else _draws(P, rng, (n, m, 2))
-    wv = np.zeros((n, 2, m, 2), np.uint64)
-    check(L.sgfhe_shortened_products(P.ctx, n, _ptr(polys), _ptr(ds), _ptr(wv)))
-    tot = _wide_sum_mod(wv, P.Q)                                          # w_tilde, v_tilde (src/fhe.jl:686-687)
-    w_t, v_t = tot[:m], tot[m:]
-    b = [_wide_to_int(new_lwes[j, n]) if j < n else 0 for j in range(m)]  # src/fhe.jl:678
-    w = [_rescale_round((-x) % P.Q, P.r, P.Q) for x in w_t]               # src/fhe.jl:689, 692
-    v = [_rescale_round((bj - x) % P.Q, P.r, P.Q) for bj, x in zip(b, v_t)]   # src/fhe.jl:690, 693
-    return Ciphertext(P, np.array(w, np.uint64), np.array(v, np.uint64))
+    w, v = np.zeros(m, np.uint64), np.zeros(m, np.uint64)
+    check(_lib.lib().sgfhe_pack_encrypted_bits(P.ctx, _ptr(bits), _ptr(draws), _ptr(ds), _ptr(w), _ptr(v)))
+    return Ciphertext(P, w, v)
 
 
 # ---- inner seams (test/internals.test.jl level) ---------------------------------------------------------
@@ -416,7 +390,7 @@ def bootstrap_trace(bkey: BootstrapKey, draws, lwe1, lwe2, n_steps: int | None =
     """_bootstrap_internal (src/fhe.jl:559-595) for one gate: outputs over Z_Q plus the accumulator after each step."""
     P = bkey.params
     bkey.upload()
-    n_steps = bkey.key.shape[0] if n_steps is None else n_steps
+    n_steps = bkey.rows if n_steps is None else n_steps
     lwe1 = np.ascontiguousarray(lwe1, np.uint64)
     lwe2 = np.ascontiguousarray(lwe2, np.uint64)
     d = None if draws is None else np.ascontiguousarray(draws, np.int64)

@@ -19,6 +19,8 @@ def bootstrap_chain(bkey, lwes1: np.ndarray, lwes2: np.ndarray, layers: int, kee
     `keep_layers` a list of such triples, one per layer (for per-layer decrypt checks as in depth.jl:65-69)."""
     import torch
     P = bkey.params
+    if layers < 1:
+        raise _lib.SgfheError("layers must be >= 1")
     bkey.upload()
     L = _lib.lib()
     dev = torch.device("cuda", P.device)

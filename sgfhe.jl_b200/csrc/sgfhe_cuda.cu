@@ -1561,9 +1561,10 @@ extern "C" int sgfhe_bkey_upload(sgfhe_ctx* c, const uint64_t* key, int32_t rows
   return SGFHE_OK;
 }
 
-extern "C" int sgfhe_bkey_token(const sgfhe_ctx* c, uint64_t* token) {
+extern "C" int sgfhe_bkey_token(const sgfhe_ctx* c, uint64_t* token, int32_t* rows) {
   if (!c || !token) return fail(SGFHE_ERR_ARG, "NULL argument");
   *token = c->key_rows > 0 ? c->key_token : 0;
+  if (rows) *rows = c->key_rows;
   return SGFHE_OK;
 }
 
@@ -1770,50 +1771,81 @@ extern "C" int sgfhe_shortened_products(sgfhe_ctx* c, int32_t count, const uint6
   return SGFHE_OK;
 }
 
-// pack_encrypted_bits(bkey, rng|nothing, enc_bits) (src/fhe.jl:660-696), every stage on the device:
-//   n internal bootstraps of (trivial(1), bit_i) keeping the AND output over Z_Q (:670-673), transposition into n polynomials
-//   of length m (:675-678), n shortened external products against key rows i (:683-684), the two sums, negate / subtract
-//   (:686-690) and ModRed to r (:692-693).
+// pack_encrypted_bits (src/fhe.jl:660-696) on the device.  Arena layout shared by the two entry points below, in uint64
+// words: triv | bits | and, or, xor (wide, [n][n+1][2] each) | polys [n][m][2] | wv [n][2][m][2] | w, v [m] | dummy | draws
+struct PackLayout { size_t triv, bits, o_and, o_or, o_xor, polys, wv, w, v, dummy, db, ds, total; };
+static PackLayout pack_layout(size_t n, size_t m, size_t db_bytes, size_t ds_bytes) {
+  PackLayout L; const size_t lwe_w = n * (n + 1);
+  L.triv = 0; L.bits = lwe_w; L.o_and = 2 * lwe_w; L.o_or = 4 * lwe_w; L.o_xor = 6 * lwe_w; L.polys = 8 * lwe_w;
+  L.wv = L.polys + n * m * 2; L.w = L.wv + n * 4 * m; L.v = L.w + m; L.dummy = L.v + m; L.db = L.dummy + 8;
+  L.ds = L.db + db_bytes / 8; L.total = L.ds + ds_bytes / 8;
+  return L;
+}
+// stages after the n internal bootstraps: transposition (src/fhe.jl:675-678), n shortened external products (:683-684),
+// sums, negate / subtract (:686-690), ModRed (:692-693).  d + PL.o_and holds the pre-ModRed LWEs.
+static int pack_tail_device(sgfhe_ctx* c, uint64_t* d, const PackLayout& PL, bool have_ds, cudaError_t* e) {
+  const size_t n = c->hp.n, m = c->hp.m;
+  pack_transpose_kernel<<<(unsigned)((n * m + 255) / 256), 256>>>((int)n, (int)m, d + PL.o_and, d + PL.polys);
+  ++g_launches;
+  *e = cudaGetLastError();
+  if (*e != cudaSuccess) return SGFHE_OK;
+  int rc = shortened_device(c, (int)n, d + PL.polys, have_ds ? reinterpret_cast<int64_t*>(d + PL.ds) : nullptr, d + PL.wv, d + PL.dummy, nullptr);
+  if (rc) return rc;
+  pack_tail_kernel<<<(unsigned)((2 * m + 127) / 128), 128>>>(c->dc, d + PL.wv, d + PL.o_and, d + PL.w, d + PL.v);
+  ++g_launches;
+  *e = cudaGetLastError();
+  return SGFHE_OK;
+}
+
 extern "C" int sgfhe_pack_encrypted_bits(sgfhe_ctx* c, const uint64_t* enc_bits, const int64_t* draws_boot,
                                          const int64_t* draws_short, uint64_t* out_w, uint64_t* out_v) {
   if (!c || !enc_bits || !out_w || !out_v) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if ((draws_boot == nullptr) != (draws_short == nullptr)) return fail(SGFHE_ERR_ARG, "draws_boot and draws_short: both or neither");
   if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
   CK(cudaSetDevice(c->device));
   const size_t n = c->hp.n, m = c->hp.m, lwe_w = n * (n + 1);
   const size_t db_bytes = draws_boot ? n * n * 4 * m * 8 : 0, ds_bytes = draws_short ? n * m * 2 * 8 : 0;
-  // layout (uint64 words): triv | bits | and, or, xor (wide) | polys | wv | w, v | dummy | draws
-  const size_t o_triv = 0, o_bits = lwe_w, o_and = 2 * lwe_w, o_or = 4 * lwe_w, o_xor = 6 * lwe_w, o_polys = 8 * lwe_w,
-               o_wv = o_polys + n * m * 2, o_w = o_wv + n * 4 * m, o_v = o_w + m, o_dummy = o_v + m, o_db = o_dummy + 8,
-               o_ds = o_db + db_bytes / 8, total = o_ds + ds_bytes / 8;
-  int rc = ensure_arena(c, total * 8); if (rc) return rc;
+  const PackLayout PL = pack_layout(n, m, db_bytes, ds_bytes);
+  int rc = ensure_arena(c, PL.total * 8); if (rc) return rc;
   uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
   std::vector<uint64_t> triv(lwe_w, 0);
   for (size_t i = 0; i < n; ++i) triv[i * (n + 1) + n] = c->hp.Dr;       // trivial LWE encrypting 1 (src/fhe.jl:670-671)
-  cudaError_t e = cudaMemcpyAsync(d + o_triv, triv.data(), lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_bits, enc_bits, lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
-  if (e == cudaSuccess && draws_boot) e = cudaMemcpyAsync(d + o_db, draws_boot, db_bytes, cudaMemcpyHostToDevice, nullptr);
-  if (e == cudaSuccess && draws_short) e = cudaMemcpyAsync(d + o_ds, draws_short, ds_bytes, cudaMemcpyHostToDevice, nullptr);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);                // `triv` leaves scope-safe
-  if (e == cudaSuccess) rc = internal_batch_device(c, (int)n, d + o_triv, d + o_bits, draws_boot ? reinterpret_cast<int64_t*>(d + o_db) : nullptr,
-                                                   d + o_and, d + o_or, d + o_xor, nullptr);
-  if (rc == SGFHE_OK && e == cudaSuccess) {
-    pack_transpose_kernel<<<(unsigned)((n * m + 255) / 256), 256>>>((int)n, (int)m, d + o_and, d + o_polys);
-    ++g_launches;
-    e = cudaGetLastError();
-  }
-  if (rc == SGFHE_OK && e == cudaSuccess)
-    rc = shortened_device(c, (int)n, d + o_polys, draws_short ? reinterpret_cast<int64_t*>(d + o_ds) : nullptr, d + o_wv, d + o_dummy, nullptr);
-  if (rc == SGFHE_OK && e == cudaSuccess) {
-    pack_tail_kernel<<<(unsigned)((2 * m + 127) / 128), 128>>>(c->dc, d + o_wv, d + o_and, d + o_w, d + o_v);
-    ++g_launches;
-    e = cudaGetLastError();
-  }
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_w, d + o_w, m * 8, cudaMemcpyDeviceToHost, nullptr);
-  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_v, d + o_v, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  cudaError_t e = cudaMemcpyAsync(d + PL.triv, triv.data(), lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + PL.bits, enc_bits, lwe_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws_boot) e = cudaMemcpyAsync(d + PL.db, draws_boot, db_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws_short) e = cudaMemcpyAsync(d + PL.ds, draws_short, ds_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);              // `triv` is pageable: copied before it goes out of scope
+  if (e == cudaSuccess) rc = internal_batch_device(c, (int)n, d + PL.triv, d + PL.bits, draws_boot ? reinterpret_cast<int64_t*>(d + PL.db) : nullptr,
+                                                   d + PL.o_and, d + PL.o_or, d + PL.o_xor, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) rc = pack_tail_device(c, d, PL, draws_short != nullptr, &e);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_w, d + PL.w, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_v, d + PL.v, m * 8, cudaMemcpyDeviceToHost, nullptr);
   const cudaError_t es = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = es;
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("pack_encrypted_bits: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+// Test seam: the stages of pack_encrypted_bits after the n bootstraps, from given pre-ModRed LWEs (src/fhe.jl:675-693).
+extern "C" int sgfhe_pack_from_lwes(sgfhe_ctx* c, const uint64_t* new_lwes, const int64_t* draws_short, uint64_t* out_w, uint64_t* out_v) {
+  if (!c || !new_lwes || !out_w || !out_v) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  CK(cudaSetDevice(c->device));
+  const size_t n = c->hp.n, m = c->hp.m, lwe_w = n * (n + 1);
+  const size_t ds_bytes = draws_short ? n * m * 2 * 8 : 0;
+  const PackLayout PL = pack_layout(n, m, 0, ds_bytes);
+  int rc = ensure_arena(c, PL.total * 8); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
+  cudaError_t e = cudaMemcpyAsync(d + PL.o_and, new_lwes, lwe_w * 16, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess && draws_short) e = cudaMemcpyAsync(d + PL.ds, draws_short, ds_bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = pack_tail_device(c, d, PL, draws_short != nullptr, &e);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_w, d + PL.w, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_v, d + PL.v, m * 8, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("pack_from_lwes: ") + cudaGetErrorString(e));
   return SGFHE_OK;
 }
 

@@ -49,7 +49,8 @@ def bootstrap_sharded(compute, lwes1: np.ndarray, lwes2: np.ndarray, dist=None, 
 
 def broadcast_key(params, rows: int, dist, src: int = 0):
     """NCCL-broadcast the pre-transformed key from `src` into every rank's library-owned device buffer.
-    Rank `src` must have uploaded its key (BootstrapKey.upload) before the call."""
+    Rank `src` must have uploaded its key (BootstrapKey.upload) before the call.  The broadcast gives every context a
+    new key token: afterwards use `BootstrapKey.resident(params)` (or `bkey.rebind()` on the root's own key object)."""
     import torch
     L = _lib.lib()
     dptr, nbytes = C.c_void_p(), C.c_uint64()

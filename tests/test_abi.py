@@ -92,19 +92,6 @@ def test_host_split_matches_oracle(sg, so):
     assert np.array_equal(got, so.split_ciphertext(OP, a, b))
 
 
-def test_wide_add_small(sg):
-    from sgfhe_jl_b200.api import _wide_add_small
-    Q = 92180593745615474572738561
-    vals = [0, 1, Q - 1, Q - 5, (1 << 64) - 1, 1 << 64, (1 << 64) + 3]
-    es = [0, 1, -1, 1024, -1024, 7, -7]
-    w = np.array([[v & (2 ** 64 - 1), v >> 64] for v in vals for _ in es], np.uint64)
-    e = np.array(es * len(vals), np.int64)
-    got = _wide_add_small(w, e, Q)
-    for k in range(len(e)):
-        want = (vals[k // len(es)] + es[k % len(es)]) % Q
-        assert int(got[k, 0]) | (int(got[k, 1]) << 64) == want
-
-
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_scheme2_params_match_oracle(sg, so, k):
     """Scheme2.Params(k), src/fhe2.jl:36-70"""

@@ -385,3 +385,290 @@ def test_transformed_key_roundtrip(env64, sg, tmp_path):
     with pytest.raises(sg.SgfheError, match="other parameters"):
         sg.BootstrapKey.load_transformed(P3, path)
     P2.close(); P3.close()
+
+
+# ---- round 2: holes named by the round-1 review ----------------------------------------------------------------------
+def _key_randomness(so, OP, seed, rows):
+    """the draws of BootstrapKey (src/fhe.jl:193-194) exactly as so.make_bkey makes them"""
+    a_rand = np.zeros((rows, 4, OP.m, 2), np.uint64)
+    e_rand = np.zeros((rows, 4, OP.m), np.int64)
+    for i in range(rows):
+        rng = np.random.default_rng([seed, 2, i])
+        a_rand[i] = so.rand_below(rng, OP.Q, (4, OP.m))
+        e_rand[i] = rng.integers(-OP.n, OP.n + 1, size=(4, OP.m), dtype=np.int64)
+    return a_rand, e_rand
+
+
+def _generate_on_device(sg, P, sk, a_rand, e_rand, chunks=1):
+    import ctypes as C
+    from sgfhe_jl_b200 import _lib
+    rows = a_rand.shape[0]
+    out = np.zeros((rows, 4, 2, P.m, 2), np.uint64)
+    skb = np.ascontiguousarray(sk, np.uint8)
+    step = -(-rows // chunks)
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        a, e, o = np.ascontiguousarray(a_rand[r0:r1]), np.ascontiguousarray(e_rand[r0:r1]), out[r0:r1]
+        _lib.check(_lib.lib().sgfhe_bkey_generate(P.ctx, skb.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p),
+                                                  e.ctypes.data_as(C.c_void_p), r0, r1 - r0, o.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+@pytest.mark.parametrize("n,rows,chunks", [(64, 64, 3), (128, 5, 1), (512, 3, 1), (1024, 2, 2)])
+def test_bkey_generate_matches_oracle(so, sg, n, rows, chunks):
+    """BootstrapKey(rng, sk) (src/fhe.jl:181-201) on the device against sgo_bkey_generate on the SAME pre-drawn a_j, e_j:
+    the coefficient form is bit-equal, and the transform-domain key the device kept drives the loop to the oracle's
+    accumulators (so the key never has to visit the host)."""
+    P, OP = sg.Params(n), so.Params(n)
+    sk = so.make_secret(OP, 7)
+    sk[:4] = (1, 0, 1, 1)                                             # both branches of + s_i G in the first rows
+    a_rand, e_rand = _key_randomness(so, OP, 7, rows)
+    e_rand[0, 0, :3] = (-n, n, 0); a_rand[0, 1, 0] = so.pack([OP.Q - 1])[0]      # edges: extreme errors, wrap at + B
+    ref = so.bkey_generate(OP, sk, np.concatenate([a_rand, np.zeros((n - rows,) + a_rand.shape[1:], np.uint64)]),
+                           np.concatenate([e_rand, np.zeros((n - rows,) + e_rand.shape[1:], np.int64)]), 0, rows)
+    got = _generate_on_device(sg, P, sk, a_rand, e_rand, chunks)
+    assert np.array_equal(got, ref)
+    bits, lwes = so.make_lwes(OP, sk, 7)
+    bk = sg.BootstrapKey.resident(P)                                  # the device copy sgfhe_bkey_generate left behind
+    assert bk.rows == rows
+    steps = min(rows, 3)
+    ga, go, gx, gtr = sg.bootstrap_trace(bk, None, lwes[1], lwes[2], n_steps=steps)
+    ra, ro, rx, rtr = so.bootstrap_internal(OP, ref, lwes[1], lwes[2], n_steps=steps, trace=True, fast=True)
+    assert np.array_equal(gtr, rtr) and np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
+    P.close()
+
+
+def test_bkey_generate_then_gates_p64(so, sg):
+    """the mirrored constructor BootstrapKey(rng, sk) end to end: gates on the device-generated key decrypt correctly and
+    equal the oracle run on the coefficient form the device reports (keep_coefficients=True)"""
+    P, OP = sg.Params(64), so.Params(64)
+    rng = np.random.default_rng(77)
+    sk = sg.PrivateKey(P, rng)
+    bkey = sg.BootstrapKey(rng, sk, keep_coefficients=True)
+    bits, lwes = so.make_lwes(OP, sk.key, 3)
+    outs = sg.bootstrap_batch(bkey, None, lwes[:8], lwes[8:16])
+    ref = so.bootstrap_batch(OP, bkey.key, lwes[:8], lwes[8:16], literal=False, threads=4)
+    for o, r in zip(outs, ref):
+        assert np.array_equal(o, r)
+    for g in range(8):
+        y1, y2 = int(bits[g]), int(bits[8 + g])
+        assert tuple(so.decrypt_lwe(OP, sk.key, o[g]) for o in outs) == (y1 & y2, y1 | y2, y1 ^ y2)
+    P.close()
+
+
+def test_two_keys_on_one_params(so, sg):
+    """a context holds one key: using a key object whose device copy was replaced re-uploads it (coefficient form kept) or
+    raises (none kept) -- never runs silently with the other key (round-1 advisor finding)"""
+    P, OP = sg.Params(64), so.Params(64)
+    sk = so.make_secret(OP, 0)
+    _, lwes = so.make_lwes(OP, sk, 0)
+    k1, k2 = so.make_bkey(OP, sk, 0), so.make_bkey(OP, sk, 5)
+    b1, b2 = sg.BootstrapKey(params=P, key=k1), sg.BootstrapKey(params=P, key=k2)
+    o1 = sg.bootstrap_batch(b1, None, lwes[:2], lwes[2:4])
+    o2 = sg.bootstrap_batch(b2, None, lwes[:2], lwes[2:4])
+    o1b = sg.bootstrap_batch(b1, None, lwes[:2], lwes[2:4])          # b2 replaced b1 on the device in between
+    assert all(np.array_equal(a, b) for a, b in zip(o1, o1b))
+    assert not all(np.array_equal(a, b) for a, b in zip(o1, o2))
+    for o, k in ((o1, k1), (o2, k2)):
+        ref = so.bootstrap(OP, k, lwes[0], lwes[2])
+        assert all(np.array_equal(x[0], r) for x, r in zip(o, ref))
+    rng = np.random.default_rng(3)
+    skg = sg.PrivateKey(P, rng)
+    g = sg.BootstrapKey(rng, skg)                                    # device-generated, no coefficient form kept
+    sg.bootstrap_batch(b1, None, lwes[:1], lwes[1:2])
+    with pytest.raises(sg.SgfheError, match="replaced by another key"):
+        sg.bootstrap_batch(g, None, lwes[:1], lwes[1:2])
+    P.close()
+
+
+def test_split_n_equals_m_and_decrypt_match_oracle(env64, so, sg):
+    """split_ciphertext of a length-m Ciphertext (src/fhe.jl:287-290 with extract's wrap-around branch, :237-244) against
+    sgo_split_rlwe, and decrypt(::EncryptedBit) (:504-507) against sgo_decrypt_lwe, row by row"""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    rng = np.random.default_rng(12)
+    for N in (OP.n, OP.m):
+        a = rng.integers(0, OP.r, size=N, dtype=np.uint64)
+        b = rng.integers(0, OP.r, size=N, dtype=np.uint64)
+        a[:3] = (0, OP.r - 1, 1); a[-2:] = (0, OP.r - 1)             # zero stays zero under the negated wrap-around
+        ct = sg.Ciphertext(P, a, b) if N == OP.m else sg.PackedCiphertext(P, a, b)
+        got = sg.split_ciphertexts([ct])
+        assert np.array_equal(got, so.split_rlwe(OP, a, b))
+    key_obj = type("K", (), {"params": P, "key": sk})()
+    dec = sg.decrypt_bits(key_obj, lwes)
+    assert dec.tolist() == [bool(so.decrypt_lwe(OP, sk, l)) for l in lwes]
+    assert dec.tolist() == [bool(b_) for b_ in bits]
+
+
+@pytest.fixture(scope="module")
+def env1024(so, sg):
+    """one full paper-size key (1 GiB) shared by the tests below"""
+    OP = so.Params(1024)
+    so.set_setup_threads(16)
+    sk = so.make_secret(OP, 1)
+    key = so.make_bkey(OP, sk, 1)
+    bits, lwes = so.make_lwes(OP, sk, 1)
+    return OP, sk, key, bits, lwes
+
+
+def test_full_randomised_gate_p1024(env1024, so, sg):
+    """one FULL gate at Params(1024) with flatten(rng, ...) (src/utils.jl:198-241): 1024 x 2 x 8192 x 2 host-supplied draws
+    (268 MB, including the extreme draws +-xmax), outputs over Z_Q and over Z_r equal the oracle's"""
+    import ctypes as C
+    from sgfhe_jl_b200 import _lib
+    OP, sk, key, bits, lwes = env1024
+    P = sg.Params(1024)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    bkey.upload()
+    rng = np.random.default_rng(91)
+    xmax = OP.B // 2 * 3
+    draws = rng.integers(-xmax, xmax + 1, size=(1, OP.n, 2, OP.m, 2), dtype=np.int64)
+    draws[0, 0, 0, :4] = ((xmax, xmax), (-xmax, -xmax), (xmax, -xmax), (0, 0))
+    draws[0, 500, 1, :] = xmax; draws[0, 501, 0, :] = -xmax           # whole steps at the extremes
+    l1, l2 = lwes[5:6], lwes[900:901]
+    raw = [np.zeros((1, OP.n + 1, 2), np.uint64) for _ in range(3)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _lib.check(_lib.lib().sgfhe_bootstrap_internal_batch(P.ctx, 1, p(l1), p(l2), p(draws), *[p(o) for o in raw]))
+    ref = so.bootstrap_internal(OP, key, l1[0], l2[0], draws=draws[0], fast=True)
+    for g, r in zip(raw, ref):
+        assert np.array_equal(g[0], r)
+    outs = [np.zeros((1, OP.n + 1), np.uint64) for _ in range(3)]
+    _lib.check(_lib.lib().sgfhe_bootstrap_batch(P.ctx, 1, p(l1), p(l2), p(draws), *[p(o) for o in outs]))
+    y1, y2 = int(bits[5]), int(bits[900])
+    for o, r, want in zip(outs, ref, (y1 & y2, y1 | y2, y1 ^ y2)):
+        assert o[0].tolist() == [so.rescale(OP.r, v, OP.Q, True) for v in so.unpack(r)]      # reduce_modulus, src/fhe.jl:616-618
+        assert so.decrypt_lwe(OP, sk, o[0]) == want
+    P.close()
+
+
+@pytest.mark.parametrize("n", [128, 256, 512])
+def test_full_deterministic_gate_mid_sizes(so, sg, n):
+    """one full gate (all n steps) at every transform shape between the test size and the paper size vs so.bootstrap"""
+    P, OP = sg.Params(n), so.Params(n)
+    so.set_setup_threads(16)
+    sk = so.make_secret(OP, 2)
+    key = so.make_bkey(OP, sk, 2)
+    bits, lwes = so.make_lwes(OP, sk, 2)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    outs = sg.bootstrap_batch(bkey, None, lwes[:3], lwes[3:6])
+    ref = so.bootstrap_batch(OP, key, lwes[:3], lwes[3:6], literal=False, threads=3)
+    for o, r in zip(outs, ref):
+        assert np.array_equal(o, r)
+    for g in range(3):
+        y1, y2 = int(bits[g]), int(bits[3 + g])
+        assert tuple(so.decrypt_lwe(OP, sk, o[g]) for o in outs) == (y1 & y2, y1 | y2, y1 ^ y2)
+    if n == 512:                                                      # examples/depth.jl runs at Params(512): chained layers
+        W, layers = 3, 3
+        got = sg.bootstrap_chain(bkey, lwes[:W], lwes[W:2 * W], layers, keep_layers=True)
+        l1, l2 = lwes[:W].copy(), lwes[W:2 * W].copy()
+        for layer in range(layers):
+            r = so.bootstrap_batch(OP, key, l1, l2, literal=False, threads=3)
+            for g_, r_ in zip(got[layer], r):
+                assert np.array_equal(g_, r_), f"layer {layer}"
+            l1, l2 = r[0], r[2]
+    P.close()
+
+
+@pytest.mark.parametrize("n", [64, 1024])
+def test_worst_case_magnitudes(so, sg, n):
+    """the approximate CRT (v from the top bits of each residue) and the FP64-assisted Barrett step at the edge of their
+    bounds: every draw +-xmax, every key coefficient floor(Q/2) or floor(Q/2)+1 (centred +-Q/2), accumulator all Q-1 or
+    chosen so that every deterministic digit is at its extreme -- |sum digit * key| reaches 4m * 2B * Q/2."""
+    P, OP = sg.Params(n), so.Params(n)
+    Q, B, m = OP.Q, OP.B, OP.m
+    xmax = B // 2 * 3
+    half = so.pack([Q // 2])[0]; half1 = so.pack([Q // 2 + 1])[0]
+    full = np.broadcast_to(so.pack([Q - 1]), (m, 2)).copy()
+    s = B // 2 - 1
+    # a with both deterministic digits at +B/2 (the largest digit): a + s (1 + B) = (B - 1) + (B - 1) B
+    top = np.broadcast_to(so.pack([((B - 1) + (B - 1) * B - s * (1 + B)) % Q]), (m, 2)).copy()
+    cases = []
+    for kv in (half, half1):
+        A = np.broadcast_to(kv, (4, 2, m, 2)).copy()
+        for sign in (1, -1):
+            cases.append((full, full, A, np.full((2, m, 2), sign * xmax, np.int64)))
+        cases.append((top, top, A, None))
+        cases.append((full, top, A, None))
+    alt = np.broadcast_to(half, (4, 2, m, 2)).copy(); alt[:, :, 1::2] = half1        # alternating signs: cancellation pattern
+    d_alt = np.full((2, m, 2), xmax, np.int64); d_alt[:, 1::2] = -xmax
+    cases.append((full, full, alt, d_alt))
+    for a, b, A, draws in cases:
+        oa, ob = sg.external_product(P, draws, a, b, A)
+        ra, rb = so.external_product(a, b, A, B, Q, draws)
+        assert np.array_equal(oa, ra) and np.array_equal(ob, rb)
+    P.close()
+
+
+@pytest.mark.parametrize("name", ["golden_p64.npz", "golden_p1024_trunc.npz", "golden_p512_trunc.npz"])
+def test_gpu_reproduces_golden(so, sg, name):
+    """the committed fixtures (tests/golden/, generator make_golden.py): the GPU path reproduces every stored output and
+    the hash of every accumulator state"""
+    import hashlib, os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    n, seed, steps = int(g["n"]), int(g["seed"]), int(g["steps"])
+    P, OP = sg.Params(n), so.Params(n)
+    key = so.make_bkey(OP, g["sk"], seed, rows=steps)
+    assert sha(key) == str(g["key_sha256"])
+    bkey = sg.BootstrapKey(params=P, key=key)
+    xmax = OP.B // 2 * 3
+    rng = np.random.default_rng([seed, 9])
+    for pi in range(len(g["pairs"])):
+        for mode in ("det", "rnd"):
+            tag = f"p{pi}_{mode}"
+            if tag + "_lwe1" not in g:
+                continue
+            draws = rng.integers(-xmax, xmax + 1, size=(steps, 2, OP.m, 2), dtype=np.int64) if mode == "rnd" else None
+            a, o, x, tr = sg.bootstrap_trace(bkey, draws, g[tag + "_lwe1"], g[tag + "_lwe2"], n_steps=steps)
+            assert np.array_equal(a, g[tag + "_and_Q"]) and np.array_equal(o, g[tag + "_or_Q"]) and np.array_equal(x, g[tag + "_xor_Q"])
+            assert [sha(tr[k]) for k in range(steps)] == [str(s_) for s_ in g[tag + "_trace_sha256"]]
+            if tag + "_and_r" in g and mode == "det":
+                outs = sg.bootstrap_batch(bkey, None, g[tag + "_lwe1"][None], g[tag + "_lwe2"][None])
+                for got, want in zip(outs, (g[tag + "_and_r"], g[tag + "_or_r"], g[tag + "_xor_r"])):
+                    assert np.array_equal(got[0], want)
+    P.close()
+
+
+def test_gpu_matches_bigint_model_p64(so, sg):
+    """second, independent pin: the first two accumulation steps on the GPU against oracle/model.py (plain Python big
+    integers, Kronecker-substitution products -- shares no code with the C oracle), both flatten modes"""
+    import model as md
+    P, OP, M = sg.Params(64), so.Params(64), md.params(64)
+    sk = so.make_secret(OP, 4)
+    steps = 2
+    key = so.make_bkey(OP, sk, 4, rows=steps)
+    _, lwes = so.make_lwes(OP, sk, 4)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    rng = np.random.default_rng(5)
+    xmax = OP.B // 2 * 3
+    for draws in (None, rng.integers(-xmax, xmax + 1, size=(steps, 2, OP.m, 2), dtype=np.int64)):
+        ga, go, gx, gtr = sg.bootstrap_trace(bkey, draws, lwes[7], lwes[9], n_steps=steps)
+        mtr = []
+        ma, mo, mx = md.bootstrap_internal(M, so.unpack(key), lwes[7].tolist(), lwes[9].tolist(),
+                                           None if draws is None else draws.tolist(), n_steps=steps, trace=mtr)
+        for k in range(steps):
+            assert so.unpack(gtr[k, 0]) == mtr[k][0] and so.unpack(gtr[k, 1]) == mtr[k][1]
+        assert so.unpack(ga) == ma and so.unpack(go) == mo and so.unpack(gx) == mx
+    P.close()
+
+
+def test_pack_tail_p1024(env1024, so, sg):
+    """pack_encrypted_bits' stages after the n bootstraps at paper size, on the device (sgfhe_pack_from_lwes): the
+    transposition, the n shortened products, the two sums, negate / subtract and ModRed of src/fhe.jl:675-693 from given
+    pre-ModRed LWEs equal the oracle's pack_from_lwes, both flatten modes (the bootstraps in front of it are covered at
+    Params(64) and by the gate tests)"""
+    import ctypes as C
+    from sgfhe_jl_b200 import _lib
+    OP, sk, key, bits, lwes = env1024
+    P = sg.Params(1024)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    bkey.upload()
+    rng = np.random.default_rng(17)
+    new_lwes = so.rand_below(rng, OP.Q, (OP.n, OP.n + 1))
+    xmax = OP.B // 2 * 3
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    for ds in (None, rng.integers(-xmax, xmax + 1, size=(OP.n, OP.m, 2), dtype=np.int64)):
+        w, v = np.zeros(OP.m, np.uint64), np.zeros(OP.m, np.uint64)
+        _lib.check(_lib.lib().sgfhe_pack_from_lwes(P.ctx, p(new_lwes), p(ds), p(w), p(v)))
+        rw, rv = so.pack_from_lwes(OP, key, new_lwes, ds)
+        assert np.array_equal(w, rw) and np.array_equal(v, rv)
+    P.close()
