@@ -120,12 +120,10 @@ class ClockSampler:
 # CPU arm: the oracle (a C port of the reference's algorithm; the reference itself is Julia + DarkIntegers,
 # neither present in this image) -- bench.py may execute oracle/ only here and in cpu_baseline.
 # ----------------------------------------------------------------------------------------------------------
-def cpu_gates_per_s(n: int, target_s: float, threads: int | None = None) -> dict:
-    import sgfhe_oracle as so
-    so.build()
-    OP = so.Params(n)
-    threads = threads or os.cpu_count() or 1
-    so.set_setup_threads(threads)
+def _cpu_sample(so, OP, n: int, threads: int, target_s: float) -> dict:
+    """`threads` gates side by side, one per thread, literal formulation; all n steps when that fits the time budget,
+    otherwise the first `steps` of them, extrapolated linearly over the strictly sequential loop (src/fhe.jl:579-582)."""
+    so.set_setup_threads(max(threads, os.cpu_count() or 1))
     sk = so.make_secret(OP, 1)
     probe = min(OP.n, 4)
     key = so.make_bkey(OP, sk, 1, rows=probe)
@@ -134,17 +132,34 @@ def cpu_gates_per_s(n: int, target_s: float, threads: int | None = None) -> dict
     t0 = time.perf_counter()
     so.bootstrap_batch(OP, key, l1, l2, n_steps=probe, literal=True, threads=threads)
     per_step = (time.perf_counter() - t0) / probe
-    steps = int(max(probe, min(OP.n, target_s / max(per_step, 1e-9))))
+    steps = OP.n if per_step * OP.n <= 1.5 * target_s else int(max(probe, min(OP.n, target_s / max(per_step, 1e-9))))
     if steps > probe:
         key = so.make_bkey(OP, sk, 1, rows=steps)
     t0 = time.perf_counter()
     so.bootstrap_batch(OP, key, l1, l2, n_steps=steps, literal=True, threads=threads)
     dt = time.perf_counter() - t0
-    gates = threads * steps / OP.n                     # linear extrapolation over the n sequential steps
+    gates = threads * steps / OP.n
+    how = "all %d accumulation steps (full gates)" % OP.n if steps == OP.n else \
+        "first %d of %d accumulation steps, extrapolated linearly in steps" % (steps, OP.n)
     return {"value": gates / dt, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
-            "sample": f"{threads} gates x first {steps} of {OP.n} accumulation steps at Params({n}), literal "
-                      f"24-NTT/step formulation (fhe.jl:579-582), {threads} threads, extrapolated linearly in steps; "
-                      "C port of SGFHE.jl's algorithm (Julia/DarkIntegers unavailable in this image)"}
+            "sample": f"{threads} gate(s) x {how} at Params({n}), literal 24-NTT/step formulation (fhe.jl:579-582), "
+                      f"{threads} thread(s); C port of SGFHE.jl's algorithm (Julia/DarkIntegers unavailable in this image)"}
+
+
+def cpu_gates_per_s(n: int, target_s: float, threads: int | None = None, with_single: bool = True) -> dict:
+    """The CPU arm.  `value` is the all-threads figure (independent gates side by side: the most the host can do);
+    `single_thread` is the figure closest to the reference itself, which is single-threaded (no Threads / Distributed
+    anywhere in src/)."""
+    import sgfhe_oracle as so
+    so.build()
+    OP = so.Params(n)
+    threads = threads or os.cpu_count() or 1
+    out = _cpu_sample(so, OP, n, threads, target_s)
+    out["host_cores"] = os.cpu_count()
+    if with_single and threads > 1:
+        one = _cpu_sample(so, OP, n, 1, max(target_s / 3, 3.0))
+        out["single_thread"] = {k: one[k] for k in ("value", "unit", "cores", "seconds", "sample")}
+    return out
 
 
 def run_reference(args) -> None:
@@ -153,12 +168,12 @@ def run_reference(args) -> None:
         return
     per_step_s = 20.0
     for _ in range(args.warmup):
-        cpu_gates_per_s(args.n, 2.0)
+        cpu_gates_per_s(args.n, 2.0, args.cpu_threads, with_single=False)
     vals = []
     t0 = time.perf_counter()
     last = None
-    for _ in range(args.steps):
-        last = cpu_gates_per_s(args.n, per_step_s)
+    for k in range(args.steps):
+        last = cpu_gates_per_s(args.n, per_step_s, args.cpu_threads, with_single=(k == args.steps - 1))
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
@@ -197,6 +212,10 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, batch = args.n, args.batch
+    if args.scaling == "strong":                         # --batch is the whole job: this rank's contiguous share of it
+        from sgfhe_jl_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(args.batch, world)[rank]
+        batch = hi - lo
     P = sg.Params(n, device=local)
     L = _lib.lib()
     # ---- key: generated and pre-transformed on rank 0, NCCL-broadcast in NTT form --------
@@ -295,7 +314,7 @@ def run_ours(args) -> None:
     verified = bool(int(okt[0]))
 
     if rank == 0:
-        total_gates = batch * world * args.steps
+        total_gates = (args.batch if args.scaling == "strong" else batch * world) * args.steps
         value = total_gates / (dev_ms / 1e3)
         e2e = total_gates / (e2e_ms / 1e3)
         qbits = P.Q.bit_length()
@@ -308,9 +327,10 @@ def run_ours(args) -> None:
         waves = -(-batch // 148)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32 (RNS residues of Z_Q, exact)", "data": "synthetic",
-            "config": {"workload": f"Params({n}) (m={P.m}, {qbits}-bit Q) batch of {batch} random gate bootstraps per GPU, rng=nothing",
+            "config": {"workload": f"Params({n}) (m={P.m}, {qbits}-bit Q) batch of {batch} random gate bootstraps per GPU, rng=nothing" +
+                                   (f" (strong scaling: {args.batch} gates in total)" if args.scaling == "strong" else ""),
                        "n": n, "batch_per_gpu": batch, "parallelism": f"gates sharded over {world} GPU(s), key NCCL-broadcast once",
                        "l2": "working set (pre-transformed key %.2f GB + per-gate scratch) is larger than L2; no flush needed" % (key_bytes / 1e9)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * h1.numel() * 8), "d2h_bytes_per_step": int(3 * h1.numel() * 8)},
@@ -335,20 +355,22 @@ def run_ours(args) -> None:
             pb = int(os.environ.get("SGFHE_PM_BATCH", "2368"))       # 16 products per SM: no partial wave for one or two products per CTA
             pa = torch.from_numpy((np.random.default_rng(7).integers(0, 1 << 62, size=(pb, P.m, 2), dtype=np.uint64) &
                                    np.array([0xFFFFFFFFFFFFFFFF, (1 << max(qbits - 65, 0)) - 1], np.uint64)).view(np.int64)).cuda()
+            pb2 = torch.from_numpy((np.random.default_rng(8).integers(0, 1 << 62, size=(pb, P.m, 2), dtype=np.uint64) &
+                                    np.array([0xFFFFFFFFFFFFFFFF, (1 << max(qbits - 65, 0)) - 1], np.uint64)).view(np.int64)).cuda()
             po = torch.empty_like(pa)
             for _ in range(3):
-                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pa.data_ptr(), po.data_ptr(), stream.cuda_stream))
+                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pb2.data_ptr(), po.data_ptr(), stream.cuda_stream))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for _ in range(5):
-                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pa.data_ptr(), po.data_ptr(), stream.cuda_stream))
+                _lib.check(L.sgfhe_polymul_device(P.ctx, pb, pa.data_ptr(), pb2.data_ptr(), po.data_ptr(), stream.cuda_stream))
             e1.record(stream); torch.cuda.synchronize()
             out["ntt_polymul"] = {"value": 5 * pb / (e0.elapsed_time(e1) / 1e3), "unit": "polymuls/s",
-                                  "workload": f"negacyclic products in Z_Q[x]/(x^{P.m}+1), batch {pb}, both operands {qbits}-bit (sgfhe_polymul_device)"}
+                                  "workload": f"negacyclic products a * b (a != b) in Z_Q[x]/(x^{P.m}+1), batch {pb}, both operands {qbits}-bit (sgfhe_polymul_device)"}
         except Exception as ex:  # the headline number must not depend on the secondary one
             out["ntt_polymul"] = {"error": str(ex)}
         if not args.no_cpu and world == 1:
-            out["cpu_baseline"] = cpu_gates_per_s(n, args.cpu_seconds)
+            out["cpu_baseline"] = cpu_gates_per_s(n, args.cpu_seconds, args.cpu_threads)
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -357,7 +379,9 @@ def run_ours(args) -> None:
 
 def run_depth(args) -> None:
     """BASELINE.json configs[4]: examples/depth.jl -- `layers` sequential gate layers at Params(512), `batch` independent
-    bit pairs per layer and GPU, layer l+1 bootstrapping (AND_l, XOR_l); ciphertexts stay in HBM between layers."""
+    bit pairs per layer and GPU, layer l+1 bootstrapping (AND_l, XOR_l); ciphertexts stay in HBM between layers.
+    --wiring allgather: the layer outputs are all-gathered and rank r continues with the wires of rank r+1 (one NCCL
+    collective per layer); --wiring local: every rank chains its own gates, nothing is exchanged."""
     import torch
     import sgfhe_jl_b200 as sg
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -374,12 +398,17 @@ def run_depth(args) -> None:
     if world > 1:
         sg.broadcast_key(P, n, dist)
         bkey = sg.BootstrapKey.resident(P)
-    rng = np.random.default_rng([args.seed, 3, rank])
-    bits, lw = [], []
-    for _ in range((2 * W + n - 1) // n):
-        msg = rng.integers(0, 2, size=n, dtype=np.uint8)
-        lw.append(np.stack([e.lwe.flat() for e in sg.split_ciphertext(sg.encrypt(sk, rng, msg))])); bits.append(msg)
-    bits = np.concatenate(bits)[: 2 * W]; lw = np.concatenate(lw)[: 2 * W]
+
+    def inputs(r):
+        rng = np.random.default_rng([args.seed, 3, r])
+        bits, lw = [], []
+        for _ in range((2 * W + n - 1) // n):
+            msg = rng.integers(0, 2, size=n, dtype=np.uint8)
+            lw.append(np.stack([e.lwe.flat() for e in sg.split_ciphertext(sg.encrypt(sk, rng, msg))])); bits.append(msg)
+        return np.concatenate(bits)[: 2 * W], np.concatenate(lw)[: 2 * W]
+
+    bits, lw = inputs(rank)
+    wiring = args.wiring if world > 1 else "local"
     for _ in range(args.warmup):
         sg.bootstrap_chain(bkey, lw[:W], lw[W:], 1)
     torch.cuda.synchronize()
@@ -387,10 +416,14 @@ def run_depth(args) -> None:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        outs = sg.bootstrap_chain(bkey, lw[:W], lw[W:], layers)
+        outs = sg.bootstrap_chain(bkey, lw[:W], lw[W:], layers, dist=dist, wiring=wiring)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    y1, y2 = bits[:W].astype(np.int64), bits[W:].astype(np.int64)
+    # plaintext circuit: after every exchanged layer rank r holds the wires of rank r+1, i.e. after `layers` layers the
+    # wires that started on rank (r + layers - 1) % world (the last layer's outputs are not exchanged)
+    src = (rank + layers - 1) % world if wiring == "allgather" else rank
+    sbits = bits if src == rank else inputs(src)[0]
+    y1, y2 = sbits[:W].astype(np.int64), sbits[W:].astype(np.int64)
     for _ in range(layers):
         y1, y2 = y1 & y2, y1 ^ y2                                   # depth.jl:71-75
     skb = sk.key.astype(bool)
@@ -405,10 +438,47 @@ def run_depth(args) -> None:
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u32 (RNS residues of Z_Q, exact)", "data": "synthetic",
                           "config": {"workload": f"examples/depth.jl chain at Params({n}): {layers} sequential layers x {W} gates per GPU, "
-                                                 "(AND, XOR) fed back in, ciphertexts resident in HBM", "n": n, "batch_per_gpu": W, "layers": layers},
+                                                 "(AND, XOR) fed back in, ciphertexts resident in HBM", "n": n, "batch_per_gpu": W, "layers": layers,
+                                     "wiring": wiring + (" (one all-gather of the layer outputs per layer; rank r continues with the wires of rank r+1)"
+                                                         if wiring == "allgather" else " (no exchange between ranks)")},
                           "verified": bool(float(t[1]) == 0.0)}))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_pack(args) -> None:
+    """pack_encrypted_bits (src/fhe.jl:660-696) through the public host entry point sgfhe_pack_encrypted_bits: one call = n
+    internal bootstraps + n shortened external products + the sums and ModRed, all on the device.  `--steps` calls are timed
+    (host buffers, copies inside the timed region); every packed ciphertext is decrypted (src/fhe.jl:471-494) and compared
+    with the plaintext bits."""
+    import torch
+    import sgfhe_jl_b200 as sg
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    n = args.n
+    P = sg.Params(n, device=local)
+    rng = np.random.default_rng([args.seed, 1])
+    sk = sg.PrivateKey(P, rng)
+    bkey = sg.BootstrapKey(np.random.default_rng([args.seed, 2]), sk)
+    msg = rng.integers(0, 2, size=n, dtype=np.uint8)
+    ebits = sg.split_ciphertext(sg.encrypt(sk, rng, msg))
+    for _ in range(max(args.warmup, 1)):
+        ct = sg.pack_encrypted_bits(bkey, None, ebits)
+    l0 = sg.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ct = sg.pack_encrypted_bits(bkey, None, ebits)
+    dt = time.perf_counter() - t0
+    ok = bool(np.array_equal(sg.decrypt(sk, ct), msg.astype(bool)))
+    print(json.dumps({"metric": "pack_encrypted_bits calls/sec", "value": args.steps / dt, "unit": "packs/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "u32 (RNS residues of Z_Q, exact)", "data": "synthetic",
+                      "gpu_launches": int(sg.launch_count() - l0),
+                      "gates_per_s_equivalent": n * args.steps / dt,
+                      "config": {"workload": f"pack_encrypted_bits at Params({n}), rng=nothing: {n} internal bootstraps + {n} shortened "
+                                             "external products + sums + ModRed per call, host buffers in and out", "n": n},
+                      "verified": ok}))
 
 
 def main():
@@ -422,11 +492,19 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--workload", default="gates", choices=["gates", "depth"], help="depth = BASELINE configs[4] (use --n 512 --batch W --layers L)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores); a one-thread figure is reported next to it")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --batch is the TOTAL over all GPUs")
+    ap.add_argument("--wiring", default="local", choices=["local", "allgather"], help="depth workload: layer inputs from this rank only, or all-gathered and permuted across ranks")
+    ap.add_argument("--workload", default="gates", choices=["gates", "depth", "pack"],
+                    help="depth = BASELINE configs[4] (use --n 512 --batch W --layers L); pack = pack_encrypted_bits calls (src/fhe.jl:660-696)")
     ap.add_argument("--layers", type=int, default=100)
     args = ap.parse_args()
+    args.cpu_threads = args.cpu_threads or None
     if args.workload == "depth" and args.impl == "ours":
         run_depth(args)
+        return
+    if args.workload == "pack" and args.impl == "ours":
+        run_pack(args)
         return
     if args.impl == "reference":
         run_reference(args)

@@ -550,7 +550,8 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
             else { dl[(jj + 1) & 1][k] = S.diglo[jn * m + tid + k * T]; dh[(jj + 1) & 1][k] = S.dighi[jn * m + tid + k * T]; }
           }
         }
-        if (jj == 2) __syncthreads();                    // previous prime's residue store has left buffers 0,1
+        // no barrier before buffers 0,1 are overwritten: their last reader (the previous prime's residue store) read, in
+        // this same thread, exactly the addresses st + k T that are written here
         uint32_t x[R0];
         if constexpr (HF) {
           head_stage1_f64<R0>(dd[jj & 1], x, fp, fpinv, fw, fwp, fc);

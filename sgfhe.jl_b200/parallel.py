@@ -47,6 +47,19 @@ def bootstrap_sharded(compute, lwes1: np.ndarray, lwes2: np.ndarray, dist=None, 
     return tuple(full)
 
 
+def exchange_layer(t_and, t_xor, dist, shift: int = 1):
+    """Layered-circuit wiring across ranks: all-gather the (AND, XOR) outputs of one layer -- torch tensors
+    [W, n+1] on every rank, CUDA under NCCL or CPU under gloo -- and return the pair of rank (rank + shift) % world as this
+    rank's next inputs.  One collective per layer; the two tensors travel as one buffer."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.stack([t_and, t_xor]).contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    src = parts[(rank + shift) % world]
+    return src[0].contiguous(), src[1].contiguous()
+
+
 def broadcast_key(params, rows: int, dist, src: int = 0):
     """NCCL-broadcast the pre-transformed key from `src` into every rank's library-owned device buffer.
     Rank `src` must have uploaded its key (BootstrapKey.upload) before the call.  The broadcast gives every context a

@@ -46,6 +46,14 @@ def _worker(rank, world, port, q):
         lo, hi = sg.shard_bounds(5, world)[rank]
         ok = all(np.array_equal(f, r) for f, r in zip(full, ref)) and \
             all(np.array_equal(x, r[lo:hi]) for x, r in zip(local, ref))
+        # layered-circuit wiring across ranks: after the exchange rank r holds rank r+1's (AND, XOR)
+        import torch
+        mine = compute(l1[lo:hi][:2], l2[lo:hi][:2])     # two gates per rank so both ranks send the same shape
+        t_and, t_xor = torch.from_numpy(mine[0].view(np.int64).copy()), torch.from_numpy(mine[2].view(np.int64).copy())
+        n_and, n_xor = sg.exchange_layer(t_and, t_xor, dist)
+        olo, ohi = sg.shard_bounds(5, world)[(rank + 1) % world]
+        other = compute(l1[olo:ohi][:2], l2[olo:ohi][:2])
+        ok = ok and np.array_equal(n_and.numpy().view(np.uint64), other[0]) and np.array_equal(n_xor.numpy().view(np.uint64), other[2])
         q.put((rank, bool(ok), (lo, hi)))
     finally:
         dist.destroy_process_group()
