@@ -105,6 +105,20 @@ int sgfhe_bootstrap_batch_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* 
                                  const uint64_t* d_lwe2, const int64_t* d_draws, uint64_t* d_out_and,
                                  uint64_t* d_out_or, uint64_t* d_out_xor, void* stream);
 
+/* bootstrap(bkey, rng, ...) with the flatten draws made ON THE DEVICE by a counter-based generator (Philox4x32-10 keyed by
+ * `seed`, counter = (coefficient, 2 step + polynomial, gate0 + gate index)): the randomised mode without 268 MB of host
+ * draws per gate at Params(1024).  Each draw is uniform on [-xmax, xmax] as at src/utils.jl:210-216, 229, but the stream is
+ * not that of any Julia RNG -- use sgfhe_bootstrap_batch with host draws where the reference's exact stream matters.
+ * seed != 0; gate0 lets sharded or successive batches use disjoint streams. */
+int sgfhe_bootstrap_batch_rng(sgfhe_ctx* ctx, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2, uint64_t seed,
+                              uint64_t gate0, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor);
+int sgfhe_bootstrap_batch_rng_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* d_lwe1, const uint64_t* d_lwe2,
+                                     uint64_t seed, uint64_t gate0, uint64_t* d_out_and, uint64_t* d_out_or,
+                                     uint64_t* d_out_xor, void* stream);
+/* Test seam: the draws that generator makes for steps step0..step0+steps-1 of gate `gate`: host int64 [steps][2][m][2],
+ * the layout sgfhe_bootstrap_batch takes for one gate. */
+int sgfhe_device_draws(sgfhe_ctx* ctx, uint64_t seed, uint64_t gate, int32_t step0, int32_t steps, int64_t* out);
+
 /* _bootstrap_internal for one gate with the accumulator after every step
  * (src/fhe.jl:559-595; loop body src/fhe.jl:579-582).  n_steps <= uploaded rows.
  * draws: NULL or [n_steps][2][m][2].  trace: NULL or [n_steps][2][m][2] uint64 (a then b, wide).
@@ -173,6 +187,35 @@ int sgfhe_rns2_op(int32_t device, int32_t op, uint64_t count, const uint64_t* a1
 int sgfhe_rns2_op_device(int32_t device, int32_t op, uint64_t count, const uint64_t* d_a1, const uint64_t* d_a2,
                          const uint64_t* d_b1, const uint64_t* d_b2, uint64_t M1, uint64_t M2, uint64_t* d_o1,
                          uint64_t* d_o2, void* stream);
+
+/* Scheme 2 polynomial arithmetic and key generation (K11).  Ring elements are RNS2Number{UInt64, B, B'} = (v mod B,
+ * v mod B') (src/rns.jl:8-24); polynomials live in (Z_B x Z_B')[x]/(x^m+1) with m = Scheme2.Params(k).m (2048..32768).
+ * Planar layout: limb 1 and limb 2 of a batch of polynomials are separate arrays [count][m] of canonical residues.
+ * NO bootstrap exists upstream for this scheme (src/fhe2.jl:1-7); these entry points cover what does exist. */
+typedef struct sgfhe_s2_ctx sgfhe_s2_ctx;
+int sgfhe_s2_ctx_create(int32_t k, int32_t device, sgfhe_s2_ctx** out);      /* Scheme2.Params(k) + twiddles, src/fhe2.jl:36-70 */
+int sgfhe_s2_ctx_destroy(sgfhe_s2_ctx* ctx);
+int sgfhe_s2_params_get(const sgfhe_s2_ctx* ctx, sgfhe_scheme2_params* out);
+/* out = a * b, negacyclic, limb-wise (Polynomial{RNS2Number} `*` as called at src/fhe2.jl:124 with src/rns.jl:51-52): host */
+int sgfhe_s2_polymul(sgfhe_s2_ctx* ctx, int32_t batch, const uint64_t* a1, const uint64_t* a2, const uint64_t* b1,
+                     const uint64_t* b2, uint64_t* o1, uint64_t* o2);
+/* same with device buffers, asynchronous on `stream`; a and b are OVERWRITTEN by their transforms; b_broadcast != 0: one
+ * polynomial b multiplies every a[i] */
+int sgfhe_s2_polymul_device(sgfhe_s2_ctx* ctx, int32_t batch, uint64_t* d_a1, uint64_t* d_a2, uint64_t* d_b1, uint64_t* d_b2,
+                            int32_t b_broadcast, uint64_t* d_o1, uint64_t* d_o2, void* stream);
+/* forward (inverse = 0) or inverse negacyclic transform of `count` polynomials per limb, in place, device buffers; the
+ * transform domain is in bit-reversed order, residues canonical */
+int sgfhe_s2_ntt_device(sgfhe_s2_ctx* ctx, int32_t inverse, int32_t count, uint64_t* d_x1, uint64_t* d_x2, void* stream);
+/* the 8 multiply-accumulates of an external product in the transform domain (the shape of src/fhe.jl:527-528 over
+ * RNS2Number): out[g][c] = sum_j d[g][j] . K[g][j][c]; d [count][4][m], K [count][4][2][m], out [count][2][m] per limb */
+int sgfhe_s2_mac8_device(sgfhe_s2_ctx* ctx, int32_t count, const uint64_t* d_d1, const uint64_t* d_d2, const uint64_t* d_k1,
+                         const uint64_t* d_k2, uint64_t* d_o1, uint64_t* d_o2, void* stream);
+/* Scheme2.BootstrapKey(rng, sk) (src/fhe2.jl:104-131) on the device.  sk: n = 1024 bytes (0/1); a_rand: host
+ * [rows][4][m][2] wide integers below Q = B B' (rand(rng, range_Q, m), src/fhe2.jl:122); e_rand: host int64 [rows][4][m]
+ * in [-tau, tau] (src/fhe2.jl:123), both in the reference's draw order.  key_out: host [rows][4][2][m][2] uint64, the
+ * (v1, v2) pairs of key[i][j,c].coeffs[k] -- the memory layout of an Array of RNS2Number. */
+int sgfhe_s2_bkey_generate(sgfhe_s2_ctx* ctx, const uint8_t* sk, const uint64_t* a_rand, const int64_t* e_rand,
+                           int32_t row0, int32_t rows, uint64_t* key_out);
 
 /* split_ciphertext (src/fhe.jl:287-290) on the device: `count` RLWE ciphertexts over Z_r, polynomials of length N
  * (N = n for a PackedCiphertext, N = m for a Ciphertext), a and b as [count][N] uint64 -> count * n LWEs [count*n][n+1]:

@@ -323,6 +323,46 @@ def rns2_op(op: int, a1, a2, b1, b2, M1: int, M2: int):
     return o1, o2
 
 
+def rns2_polymul(a1, a2, b1, b2, M1: int, M2: int):
+    """Polynomial{RNS2Number} `*` (negacyclic; src/fhe2.jl:124 with the limb-wise product of src/rns.jl:51-52): each limb
+    is a product in Z_Mi[x]/(x^N+1), computed by the Z_Q oracle product with Q = Mi (Mi is an NTT prime, src/fhe2.jl:57-60).
+    a*, b*: uint64[N] -> (o1, o2) uint64[N]"""
+    outs = []
+    for a, b, M in ((a1, b1, M1), (a2, b2, M2)):
+        wa = np.stack([np.asarray(a, np.uint64), np.zeros(len(a), np.uint64)], axis=-1)
+        wb = np.stack([np.asarray(b, np.uint64), np.zeros(len(b), np.uint64)], axis=-1)
+        outs.append(np.ascontiguousarray(polymul(wa, wb, M)[:, 0]))
+    return outs[0], outs[1]
+
+
+def scheme2_bkey_generate(k: int, sk, a_rand, e_rand, rows: int):
+    """Scheme2.BootstrapKey (src/fhe2.jl:104-131) for key rows 0..rows-1.  sk uint8[n]; a_rand uint64[rows,4,m,2] wide
+    integers below Q = B B'; e_rand int64[rows,4,m] -> uint64[rows,4,2,m,2] (v1, v2) pairs of key[i][j,c].coeffs."""
+    S = scheme2_params(k)
+    n, m, mods = S.n, S.m, (S.B, S.Bp)
+    ext = np.zeros(m, np.uint64); ext[:n] = np.asarray(sk, np.uint64)                       # fhe2.jl:113
+    key = np.zeros((rows, 4, 2, m, 2), np.uint64)
+    aw = np.asarray(a_rand, np.uint64)
+    a_int = aw[..., 0].astype(object) + (aw[..., 1].astype(object) << 64)
+    for i in range(rows):
+        for j in range(4):
+            for l, M in enumerate(mods):
+                aj = np.array([int(v) % M for v in a_int[i, j]], np.uint64)                 # polynomial_Q, fhe2.jl:81-82
+                wa = np.stack([aj, np.zeros(m, np.uint64)], axis=-1)
+                we = np.stack([ext, np.zeros(m, np.uint64)], axis=-1)
+                pr = polymul(wa, we, M)[:, 0].astype(object)
+                bj = np.array([(int(v) + int(e)) % M for v, e in zip(pr, e_rand[i, j])], np.uint64)   # fhe2.jl:124
+                if sk[i]:                                                                   # + s_i G, fhe2.jl:125, 98-101
+                    g = (S.B % M) if (j & 1) else 1
+                    if j < 2:
+                        aj[0] = (int(aj[0]) + g) % M
+                    else:
+                        bj[0] = (int(bj[0]) + g) % M
+                key[i, j, 0, :, l] = aj
+                key[i, j, 1, :, l] = bj
+    return key
+
+
 def set_setup_threads(t: int):
     lib().sgo_set_setup_threads(int(t))
 

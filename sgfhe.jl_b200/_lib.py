@@ -23,7 +23,9 @@ SYMBOLS = [
     "sgfhe_scheme2_params_derive", "sgfhe_rns2_op", "sgfhe_rns2_op_device",
     "sgfhe_bkey_export_size", "sgfhe_bkey_export", "sgfhe_bkey_import",
     "sgfhe_split_ciphertext", "sgfhe_split_ciphertext_device", "sgfhe_decrypt_bits", "sgfhe_decrypt_bits_device",
-    "sgfhe_bkey_generate", "sgfhe_bkey_token", "sgfhe_pack_encrypted_bits", "sgfhe_pack_from_lwes",
+    "sgfhe_bkey_generate", "sgfhe_bkey_token", "sgfhe_pack_encrypted_bits", "sgfhe_pack_from_lwes", "sgfhe_bootstrap_batch_rng", "sgfhe_bootstrap_batch_rng_device", "sgfhe_device_draws",
+    "sgfhe_s2_ctx_create", "sgfhe_s2_ctx_destroy", "sgfhe_s2_params_get", "sgfhe_s2_polymul", "sgfhe_s2_polymul_device",
+    "sgfhe_s2_ntt_device", "sgfhe_s2_mac8_device", "sgfhe_s2_bkey_generate",
 ]
 
 
@@ -81,6 +83,17 @@ def lib():
         L.sgfhe_bkey_token.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
         L.sgfhe_pack_encrypted_bits.argtypes = [vp, u64p, vp, vp, u64p, u64p]
         L.sgfhe_pack_from_lwes.argtypes = [vp, u64p, vp, u64p, u64p]
+        L.sgfhe_bootstrap_batch_rng.argtypes = [vp, i32, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, u64p]
+        L.sgfhe_bootstrap_batch_rng_device.argtypes = [vp, i32, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, u64p, vp]
+        L.sgfhe_device_draws.argtypes = [vp, C.c_uint64, C.c_uint64, i32, i32, vp]
+        L.sgfhe_s2_ctx_create.argtypes = [i32, i32, C.POINTER(vp)]
+        L.sgfhe_s2_ctx_destroy.argtypes = [vp]
+        L.sgfhe_s2_params_get.argtypes = [vp, C.POINTER(Scheme2ParamsC)]
+        L.sgfhe_s2_polymul.argtypes = [vp, i32, u64p, u64p, u64p, u64p, u64p, u64p]
+        L.sgfhe_s2_polymul_device.argtypes = [vp, i32, u64p, u64p, u64p, u64p, i32, u64p, u64p, vp]
+        L.sgfhe_s2_ntt_device.argtypes = [vp, i32, i32, u64p, u64p, vp]
+        L.sgfhe_s2_mac8_device.argtypes = [vp, i32, u64p, u64p, u64p, u64p, u64p, u64p, vp]
+        L.sgfhe_s2_bkey_generate.argtypes = [vp, vp, u64p, vp, i32, i32, u64p]
         L.sgfhe_scheme2_params_derive.argtypes = [i32, C.POINTER(Scheme2ParamsC)]
         L.sgfhe_rns2_op.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p]
         L.sgfhe_rns2_op_device.argtypes = [i32, i32, C.c_uint64, u64p, u64p, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u64p, vp]

@@ -312,8 +312,20 @@ def _draws(P: Params, rng: np.random.Generator, shape) -> np.ndarray:
     return rng.integers(-xmax, xmax + 1, size=shape, dtype=np.int64)
 
 
+class DeviceRng:
+    """An `rng` argument that makes the flatten draws on the GPU (Philox4x32-10 keyed by `seed`, one stream per gate):
+    the randomised mode at sizes where host-drawn values do not fit (268 MB per gate at Params(1024)).  Not the stream of
+    any host RNG: use a numpy Generator where the caller's exact draws matter."""
+
+    def __init__(self, seed: int):
+        if not 0 < seed < (1 << 64):
+            raise SgfheError("seed must be in [1, 2^64)")
+        self.seed, self.gates_drawn = int(seed), 0
+
+
 def bootstrap_batch(bkey: BootstrapKey, rng, lwes1: np.ndarray, lwes2: np.ndarray):
-    """Batched form of `bootstrap`: lwes1, lwes2 uint64[batch, n+1] -> (and, or, xor) uint64[batch, n+1]."""
+    """Batched form of `bootstrap`: lwes1, lwes2 uint64[batch, n+1] -> (and, or, xor) uint64[batch, n+1].
+    rng: None (deterministic flatten), a numpy Generator (draws made here in the reference's order) or a DeviceRng."""
     P = bkey.params
     lwes1 = np.ascontiguousarray(lwes1, np.uint64)
     lwes2 = np.ascontiguousarray(lwes2, np.uint64)
@@ -321,8 +333,13 @@ def bootstrap_batch(bkey: BootstrapKey, rng, lwes1: np.ndarray, lwes2: np.ndarra
         raise SgfheError("LWE arrays must be [batch, n+1]")
     bkey.upload()
     batch = lwes1.shape[0]
-    draws = None if rng is None else _draws(P, rng, (batch, P.n, 2, P.m, 2))   # order: src/fhe.jl:524-525, utils.jl:257-258
     outs = [np.zeros_like(lwes1) for _ in range(3)]
+    if isinstance(rng, DeviceRng):
+        check(_lib.lib().sgfhe_bootstrap_batch_rng(P.ctx, batch, _ptr(lwes1), _ptr(lwes2), rng.seed, rng.gates_drawn,
+                                                   *[_ptr(o) for o in outs]))
+        rng.gates_drawn += batch
+        return tuple(outs)
+    draws = None if rng is None else _draws(P, rng, (batch, P.n, 2, P.m, 2))   # order: src/fhe.jl:524-525, utils.jl:257-258
     check(_lib.lib().sgfhe_bootstrap_batch(P.ctx, batch, _ptr(lwes1), _ptr(lwes2), _ptr(draws), *[_ptr(o) for o in outs]))
     return tuple(outs)
 
@@ -423,3 +440,58 @@ def rns2_op(op: str, a, b, M1: int, M2: int, device: int = 0):
     o1, o2 = np.zeros_like(arrs[0]), np.zeros_like(arrs[0])
     check(_lib.lib().sgfhe_rns2_op(device, code, arrs[0].size, *[_ptr(x) for x in arrs], M1, M2, _ptr(o1), _ptr(o2)))
     return o1, o2
+
+
+class Scheme2Context:
+    """Device context for Scheme2.Params(k) (src/fhe2.jl:36-70): polynomial arithmetic over RNS2Number and key generation.
+    Upstream defines no bootstrap for this scheme (src/fhe2.jl:1-7), so neither does this."""
+
+    def __init__(self, k: int, device: int = 0):
+        self.params = Scheme2Params(k)
+        self.device = device
+        h = C.c_void_p()
+        check(_lib.lib().sgfhe_s2_ctx_create(int(k), device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().sgfhe_s2_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def polymul(self, a, b):
+        """a * b in (Z_B x Z_B')[x]/(x^m+1), batched: a, b are pairs (v1, v2) of uint64[batch, m]."""
+        arrs = [np.ascontiguousarray(x, np.uint64) for x in (a[0], a[1], b[0], b[1])]
+        if any(x.shape != arrs[0].shape for x in arrs) or arrs[0].ndim != 2 or arrs[0].shape[1] != self.params.m:
+            raise SgfheError("operands must be pairs of [batch, m]")
+        o1, o2 = np.zeros_like(arrs[0]), np.zeros_like(arrs[0])
+        check(_lib.lib().sgfhe_s2_polymul(self._h, arrs[0].shape[0], *[_ptr(x) for x in arrs], _ptr(o1), _ptr(o2)))
+        return o1, o2
+
+    def bootstrap_key(self, sk: np.ndarray, a_rand: np.ndarray, e_rand: np.ndarray) -> np.ndarray:
+        """Scheme2.BootstrapKey from pre-drawn randomness (src/fhe2.jl:119-126): uint64[rows, 4, 2, m, 2]."""
+        a_rand = np.ascontiguousarray(a_rand, np.uint64)
+        e_rand = np.ascontiguousarray(e_rand, np.int64)
+        rows = a_rand.shape[0]
+        out = np.zeros((rows, 4, 2, self.params.m, 2), np.uint64)
+        skb = np.ascontiguousarray(sk, np.uint8)
+        check(_lib.lib().sgfhe_s2_bkey_generate(self._h, _ptr(skb), _ptr(a_rand), _ptr(e_rand), 0, rows, _ptr(out)))
+        return out
+
+
+def scheme2_bootstrap_key(ctx: Scheme2Context, rng: np.random.Generator, sk: np.ndarray, rows: int | None = None) -> np.ndarray:
+    """Scheme2.BootstrapKey(rng, sk) -- src/fhe2.jl:104-131: per row a_1..a_4 uniform below Q = B B', then e_1..e_4 uniform on
+    [-tau, tau], drawn here in the reference's order; the arithmetic runs on the device."""
+    S = ctx.params
+    rows = S.n if rows is None else rows
+    a = np.zeros((rows, 4, S.m, 2), np.uint64)
+    e = np.zeros((rows, 4, S.m), np.int64)
+    for i in range(rows):
+        a[i] = _rand_below(rng, S.Q, (4, S.m))                                     # src/fhe2.jl:122
+        e[i] = rng.integers(-S.tau, S.tau + 1, size=(4, S.m), dtype=np.int64)      # src/fhe2.jl:123
+    return ctx.bootstrap_key(sk, a, e)

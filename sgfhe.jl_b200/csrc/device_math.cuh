@@ -27,6 +27,7 @@ struct DevConst {
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
   uint64_t s46;                 // 2^46 - s: bias of the stored digit words minus the digit offset
+  uint64_t xmax;                // 3 (B / 2): draws of the randomised flatten are uniform on [-xmax, xmax] (src/utils.jl:210-216)
   double barrett_inv;           // 2^(sbits-16) / Q, scaled by (1 - 2^-40): never above the true value
   double inv35;                 // 1/35 rounded up
   uint32_t Ql[3], offl[3];      // Q and offs as 32-bit limbs

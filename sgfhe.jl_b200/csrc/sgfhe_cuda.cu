@@ -38,6 +38,7 @@ struct GateArgs {
   unsigned long long* timing;                   // NULL, or 8 phase-cycle accumulators written by CTA 0 (profiling aid)
   const uint64_t* pack_in;                      // F_PACK: [batch][m][2] wide polynomials, job g multiplies poly g with key row g
   const int64_t* pack_draws;                    // F_PACK: NULL or [batch][m][2]
+  uint64_t rng_seed, rng_gate0;                 // draws == NULL and rng_seed != 0: flatten(rng, ...) with draws made on the device (DrawSrc)
   int* work_counter;                            // NULL (gate g = blockIdx.x + k gridDim.x) or a zeroed device counter: CTAs take the next gate when they finish one
   int stagger_cycles, stagger_slots;            // CTA b starts (b % slots) * cycles late: spreads the L2-bound phases of the CTAs in time
 };
@@ -84,14 +85,44 @@ __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
   }
 }
 
+// Where flatten(rng, ...) (src/utils.jl:198-241) takes its draws rand(rng, -xmax:xmax) from.  ptr: the caller's values for
+// this step, [2][m][2] (polynomial a then b, coefficient, digit) -- the parity path, bit-exact with the reference for the
+// caller's RNG.  ptr == NULL and seed != 0: made on the device by the counter-based generator Philox4x32-10 (Salmon et al.,
+// SC'11), key = seed, counter = (coefficient, 2 step + polynomial, gate): no memory traffic, so the randomised mode is
+// usable at paper size (host draws are 268 MB per gate there).  Valid randomised ciphertexts, but a different stream
+// from any Julia RNG; the same (seed, gate, step) always gives the same draws.
+struct DrawSrc {
+  const int64_t* ptr; uint64_t seed; uint32_t gate, step;
+  __device__ __forceinline__ bool on() const { return ptr != nullptr || seed != 0; }
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// the two draws (digit 1, digit 2) of coefficient j of polynomial c: uniform on [-xmax, xmax] by multiply-shift of 64 random
+// bits (bias below 2^-18 of one value's probability)
+__device__ __forceinline__ void get_draws(const DevConst& C, const DrawSrc& d, int c, int j, int m, int64_t& x0, int64_t& x1) {
+  if (d.ptr) { x0 = d.ptr[((size_t)c * m + j) * 2]; x1 = d.ptr[((size_t)c * m + j) * 2 + 1]; return; }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)j, 2u * d.step + (uint32_t)c, d.gate, 0x53474648u),
+                                make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+  x0 = (int64_t)__umul64hi((uint64_t)r.x | ((uint64_t)r.y << 32), 2 * C.xmax + 1) - (int64_t)C.xmax;
+  x1 = (int64_t)__umul64hi((uint64_t)r.z | ((uint64_t)r.w << 32), 2 * C.xmax + 1) - (int64_t)C.xmax;
+}
+
 // gadget decomposition of accumulator polynomial c (src/utils.jl:253-264) into S.dig[2c], S.dig[2c+1]
 template <int LOGM, bool F64>
-__device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch& S, int c, const int64_t* __restrict__ draws) {
+__device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch& S, int c, const DrawSrc draws) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1;
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     const u96 v = ld96(S.acc + c * 3 * m, m, idx);
     uint64_t dp0, dp1;
-    if (draws) decompose_off_rand<KB>(C, v, draws[((size_t)c * m + idx) * 2], draws[((size_t)c * m + idx) * 2 + 1], dp0, dp1);
+    if (draws.on()) { int64_t x0, x1; get_draws(C, draws, c, idx, m, x0, x1); decompose_off_rand<KB>(C, v, x0, x1, dp0, dp1); }
     else decompose_off<KB>(C, v, dp0, dp1);
     if (F64) { S.digd[(2 * c) * m + idx] = digit_f64(dp0); S.digd[(2 * c + 1) * m + idx] = digit_f64(dp1); }
     else {
@@ -107,7 +138,7 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
 //   reduction; DEC: fused with the next step's gadget decomposition (RAND: with the caller's draws).
 template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND, bool F64>
 __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S, const uint4* sm4, int c,
-                                            const int64_t* __restrict__ draws_next, int u, u96 (&aq)[D]) {
+                                            const DrawSrc draws_next, int u, u96 (&aq)[D]) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1, SB = 6 * LOGM + 8;
   constexpr int NIT = m / T;
   const int tid = threadIdx.x;
@@ -137,7 +168,7 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
       st96(acc, m, j, res);
       if (DEC) {
         uint64_t dp0, dp1;
-        if (RAND) decompose_off_rand<KB>(C, res, draws_next[((size_t)c * m + j) * 2], draws_next[((size_t)c * m + j) * 2 + 1], dp0, dp1);
+        if (RAND) { int64_t x0, x1; get_draws(C, draws_next, c, j, m, x0, x1); decompose_off_rand<KB>(C, res, x0, x1, dp0, dp1); }
         else decompose_off<KB>(C, res, dp0, dp1);
         if (F64) { S.digd[(2 * c) * m + j] = digit_f64(dp0); S.digd[(2 * c + 1) * m + j] = digit_f64(dp1); }
         else {
@@ -155,7 +186,7 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
 // OWN: each thread reads only residues it stored itself (v4 kernel), so those loads may precede the entry barrier.
 template <int LOGM, int T, bool OWN, bool F64>
 __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
-                                           const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
+                                           const DrawSrc draws_next, int u, bool ext, bool decompose_next,
                                            unsigned long long* timing, long long& tprev) {
   constexpr int m = 1 << LOGM, L = Shape<LOGM>::L;
   const int tid = threadIdx.x;
@@ -232,13 +263,13 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
       }
     }
     if (ext) {
-      if (!decompose_next) update_poly<LOGM, T, D, true, false, false, F64>(C, S, sm4, c, nullptr, u, aq);
-      else if (draws_next) update_poly<LOGM, T, D, true, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, true, true, false, F64>(C, S, sm4, c, nullptr, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, true, false, false, F64>(C, S, sm4, c, draws_next, u, aq);
+      else if (draws_next.on()) update_poly<LOGM, T, D, true, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, true, true, false, F64>(C, S, sm4, c, draws_next, u, aq);
     } else {
-      if (!decompose_next) update_poly<LOGM, T, D, false, false, false, F64>(C, S, sm4, c, nullptr, u, aq);
-      else if (draws_next) update_poly<LOGM, T, D, false, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, false, true, false, F64>(C, S, sm4, c, nullptr, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, false, false, false, F64>(C, S, sm4, c, draws_next, u, aq);
+      else if (draws_next.on()) update_poly<LOGM, T, D, false, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, false, true, false, F64>(C, S, sm4, c, draws_next, u, aq);
     }
     __syncthreads();
     SGFHE_TICK(6);
@@ -251,7 +282,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
 template <int LOGM>
 __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                           const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
-                          const int64_t* __restrict__ draws_next, int u, bool ext, bool decompose_next,
+                          const DrawSrc draws_next, int u, bool ext, bool decompose_next,
                           uint2* tab, uint64_t* bar, uint32_t& parity, unsigned long long* timing) {
   using SH = Shape<LOGM>;
   long long tprev = timing ? clock64() : 0;
@@ -513,7 +544,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
 
 template <int LOGM, bool HF>
 __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
-                             const uint2* __restrict__ tw_f, const int64_t* __restrict__ draws_next, int u, bool ext,
+                             const uint2* __restrict__ tw_f, const DrawSrc draws_next, int u, bool ext,
                              bool decompose_next, uint2* tab, uint64_t* bar, uint32_t& parity,
                              unsigned long long* timing) {
   using S4 = Shape4<LOGM>;
@@ -707,6 +738,12 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
     const uint64_t* l2 = A.lwe2 + (size_t)g * (n + 1);
     const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
     const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
+    const uint64_t seed = A.draws ? 0 : A.rng_seed;
+    const uint32_t gid = (uint32_t)(A.rng_gate0 + (uint64_t)g);
+    auto draws_of = [&](int k) {                          // the draws of accumulation step k of this gate (none: deterministic)
+      DrawSrc d; d.ptr = dr ? dr + (size_t)(k - (pack ? 0 : A.step_begin)) * 4 * m : nullptr; d.seed = seed; d.gate = gid; d.step = (uint32_t)k;
+      return d;
+    };
     if (A.flags & F_INIT) gate_init<LOGM>(C, S, (l1[n] + l2[n]) & rmask);
     if (pack) {                                          // a = 0, b = input polynomial g: only the b-digit key rows contribute
       u96 zero; zero.x0 = zero.x1 = zero.x2 = 0;
@@ -720,15 +757,22 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
     __syncthreads();
     const int k_begin = pack ? g : A.step_begin, k_end = pack ? g + 1 : A.step_end;
     if ((A.flags & F_DECOMP) && k_begin < k_end) {
-      decompose_poly<LOGM, HF>(C, S, 0, pack ? nullptr : dr);
-      decompose_poly<LOGM, HF>(C, S, 1, pack ? (A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr) : dr);
+      DrawSrc d0 = draws_of(k_begin), d1 = d0;
+      if (pack) {                                        // shortened product: a = 0 is flattened without draws, b with its own
+        d0.ptr = nullptr; d0.seed = 0;
+        d1.ptr = A.pack_draws ? A.pack_draws + (size_t)g * 2 * m - 2 * m : nullptr;      // indexed with c = 1
+        d1.seed = A.pack_draws ? 0 : A.rng_seed; d1.step = (uint32_t)n;                 // a step index no gate uses
+      }
+      decompose_poly<LOGM, HF>(C, S, 0, d0);
+      decompose_poly<LOGM, HF>(C, S, 1, d1);
     }
     __syncthreads();
     for (int k = k_begin; k < k_end; ++k) {
       const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
       const bool more = k + 1 < k_end;
       const uint32_t* keyrow = A.keyhat + (size_t)k * C.L * 8 * m;
-      const int64_t* dn = (dr && more) ? dr + (size_t)(k + 1 - k_begin) * 4 * m : nullptr;
+      DrawSrc dn = draws_of(k + 1);
+      if (!more) { dn.ptr = nullptr; dn.seed = 0; }
       unsigned long long* tm = blockIdx.x == 0 ? A.timing : nullptr;
       if constexpr (V4) gate_step_v4<LOGM, HF>(C, S, sm, keyrow, A.tw_f, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
       else gate_step<LOGM>(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
@@ -1183,6 +1227,19 @@ __global__ void pack_tail_kernel(const __grid_constant__ DevConst C, const uint6
   }
 }
 
+// test seam: the draws DrawSrc makes on the device for (seed, gate, steps step0..), as the host would have to supply them
+__global__ void device_draws_kernel(const __grid_constant__ DevConst C, uint64_t seed, uint32_t gate, int step0, int steps,
+                                    int64_t* __restrict__ out) {
+  const int m = C.m;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)steps * 2 * m) return;
+  const int j = (int)(idx % m), c = (int)((idx / m) & 1), k = (int)(idx / ((size_t)2 * m));
+  DrawSrc d; d.ptr = nullptr; d.seed = seed; d.gate = gate; d.step = (uint32_t)(step0 + k);
+  int64_t x0, x1;
+  get_draws(C, d, c, j, m, x0, x1);
+  out[2 * idx] = x0; out[2 * idx + 1] = x1;
+}
+
 // wide [2][m][2] -> accumulator scratch (SoA limbs) and back
 __global__ void acc_load_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ ab, uint32_t* acc) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x, m = C.m;
@@ -1260,6 +1317,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   dc->barrett_inv = ldexp(1.0, dc->sbits - 16) / (double)hp.Q * (1.0 - ldexp(1.0, -40));
   dc->inv35 = nextafter(nextafter(1.0 / 35.0, 1.0), 1.0);
   dc->s46 = ((uint64_t)1 << 46) - dc->s;
+  dc->xmax = (uint64_t)(hp.B / 2 * 3);
   {
     const u128 K = ((u128)L << 30) + L + 1, KQ = K * hp.Q;                 // < 2^34 Q < 2^124
     dc->KQ[0] = (uint32_t)KQ; dc->KQ[1] = (uint32_t)(KQ >> 32); dc->KQ[2] = (uint32_t)(KQ >> 64); dc->KQ[3] = (uint32_t)(KQ >> 96);
@@ -1420,6 +1478,9 @@ static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const 
 }
 
 extern "C" const char* sgfhe_last_error(void) { return g_err.c_str(); }
+// shared with scheme2.cu (not part of the public header)
+extern "C" void sgfhe_set_error_(const char* msg) { g_err = msg; }
+extern "C" void sgfhe_count_launch_(void) { ++g_launches; }
 extern "C" uint64_t sgfhe_launch_count(void) { return g_launches.load(); }
 
 static void fill_params(const HostParams& hp, int L, sgfhe_params* out) {
@@ -1670,6 +1731,59 @@ extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const u
     return rc;
   }
   return launch_gates(c, A, (cudaStream_t)stream);
+}
+
+// bootstrap(bkey, rng, ...) with the flatten draws made on the device (DrawSrc): gate g of the batch uses the stream
+// (seed, gate0 + g).  seed != 0.
+extern "C" int sgfhe_bootstrap_batch_rng_device(sgfhe_ctx* c, int32_t batch, const uint64_t* d_lwe1, const uint64_t* d_lwe2,
+                                                uint64_t seed, uint64_t gate0, uint64_t* d_and, uint64_t* d_or, uint64_t* d_xor,
+                                                void* stream) {
+  if (!c || !d_lwe1 || !d_lwe2 || !d_and || !d_or || !d_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (seed == 0) return fail(SGFHE_ERR_ARG, "seed must be non-zero (0 selects the deterministic flatten)");
+  if (c->key_rows != c->hp.n) return fail(SGFHE_ERR_STATE, "no complete bootstrap key uploaded");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  GateArgs A; memset(&A, 0, sizeof A);
+  A.lwe1 = d_lwe1; A.lwe2 = d_lwe2; A.out_and = d_and; A.out_or = d_or; A.out_xor = d_xor; A.rng_seed = seed; A.rng_gate0 = gate0;
+  A.batch = batch; A.step_begin = 0; A.step_end = c->hp.n; A.draw_steps = c->hp.n; A.flags = F_INIT | F_DECOMP | F_FINAL;
+  return launch_gates(c, A, (cudaStream_t)stream);
+}
+
+extern "C" int sgfhe_bootstrap_batch_rng(sgfhe_ctx* c, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2, uint64_t seed,
+                                         uint64_t gate0, uint64_t* out_and, uint64_t* out_or, uint64_t* out_xor) {
+  if (!c || !lwe1 || !lwe2 || !out_and || !out_or || !out_xor) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (batch < 0) return fail(SGFHE_ERR_ARG, "negative batch");
+  if (batch == 0) return SGFHE_OK;
+  CK(cudaSetDevice(c->device));
+  const size_t w = (size_t)batch * (c->hp.n + 1);
+  int rc = ensure_arena(c, 5 * w * 8); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
+  cudaError_t e = cudaMemcpyAsync(d, lwe1, w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + w, lwe2, w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = sgfhe_bootstrap_batch_rng_device(c, batch, d, d + w, seed, gate0, d + 2 * w, d + 3 * w, d + 4 * w, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_and, d + 2 * w, w * 8, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_or, d + 3 * w, w * 8, cudaMemcpyDeviceToHost, nullptr);
+  if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_xor, d + 4 * w, w * 8, cudaMemcpyDeviceToHost, nullptr);
+  const cudaError_t es = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = es;
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_batch_rng: ") + cudaGetErrorString(e));
+  return SGFHE_OK;
+}
+
+// test seam: the draws the device generator makes for accumulation steps step0 .. step0+steps-1 of gate `gate`
+extern "C" int sgfhe_device_draws(sgfhe_ctx* c, uint64_t seed, uint64_t gate, int32_t step0, int32_t steps, int64_t* out) {
+  if (!c || !out) return fail(SGFHE_ERR_ARG, "NULL argument");
+  if (seed == 0 || step0 < 0 || steps < 1) return fail(SGFHE_ERR_ARG, "bad seed / step range");
+  CK(cudaSetDevice(c->device));
+  const size_t count = (size_t)steps * 2 * c->hp.m;
+  int rc = ensure_arena(c, count * 16); if (rc) return rc;
+  device_draws_kernel<<<(unsigned)((count + 255) / 256), 256>>>(c->dc, seed, (uint32_t)gate, step0, steps, reinterpret_cast<int64_t*>(c->d_arena));
+  ++g_launches;
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, c->d_arena, count * 16, cudaMemcpyDeviceToHost));
+  return SGFHE_OK;
 }
 
 extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t* lwe1, const uint64_t* lwe2,

@@ -672,3 +672,164 @@ def test_pack_tail_p1024(env1024, so, sg):
         rw, rv = so.pack_from_lwes(OP, key, new_lwes, ds)
         assert np.array_equal(w, rw) and np.array_equal(v, rv)
     P.close()
+
+
+# ---- Scheme 2 (src/fhe2.jl, src/rns.jl): what exists upstream -- there is no reference bootstrap for it -----------------
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_scheme2_polymul_matches_oracle(so, sg, k):
+    """Polynomial{RNS2Number} `*` at the ring degree of Scheme2.Params(k) (m = 2048 .. 32768; one- and two-pass
+    transforms): random and edge operands against the oracle's limb-wise product"""
+    ctx = sg.Scheme2Context(k)
+    S = ctx.params
+    rng = np.random.default_rng(70 + k)
+    nb = 3
+    a1 = rng.integers(0, S.B, size=(nb, S.m), dtype=np.uint64); a2 = rng.integers(0, S.Bp, size=(nb, S.m), dtype=np.uint64)
+    b1 = rng.integers(0, S.B, size=(nb, S.m), dtype=np.uint64); b2 = rng.integers(0, S.Bp, size=(nb, S.m), dtype=np.uint64)
+    a1[1] = S.B - 1; a2[1] = S.Bp - 1; b1[1] = S.B - 1; b2[1] = S.Bp - 1        # all coefficients at the maximum
+    a1[2] = 0; a2[2] = 0; a1[2, S.m - 1] = 1; a2[2, S.m - 1] = 1                # x^(m-1): a rotation with wrap-around sign
+    o1, o2 = ctx.polymul((a1, a2), (b1, b2))
+    for i in range(nb):
+        r1, r2 = so.rns2_polymul(a1[i], a2[i], b1[i], b2[i], S.B, S.Bp)
+        assert np.array_equal(o1[i], r1) and np.array_equal(o2[i], r2), f"product {i}"
+    ctx.close()
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_scheme2_transform_and_mac(so, sg, k):
+    """forward + inverse transform is the identity; the 8 multiply-accumulates of an external product done in the transform
+    domain and transformed back equal the sum of the oracle's products (src/fhe.jl:527-528 shape over RNS2Number)"""
+    import ctypes as C
+    import torch
+    from sgfhe_jl_b200 import _lib
+    ctx = sg.Scheme2Context(k)
+    S, L = ctx.params, _lib.lib()
+    rng = np.random.default_rng(80 + k)
+    mods = (S.B, S.Bp)
+    d = [rng.integers(0, M, size=(1, 4, S.m), dtype=np.uint64) for M in mods]           # digit polynomials
+    K = [rng.integers(0, M, size=(1, 4, 2, S.m), dtype=np.uint64) for M in mods]        # key tile
+    dev = lambda a: torch.from_numpy(a.view(np.int64).copy()).cuda()
+    td, tK = [dev(x) for x in d], [dev(x) for x in K]
+    t0 = [x.clone() for x in td]
+    _lib.check(L.sgfhe_s2_ntt_device(ctx._h, 0, 4, td[0].data_ptr(), td[1].data_ptr(), None))
+    back = [x.clone() for x in td]
+    _lib.check(L.sgfhe_s2_ntt_device(ctx._h, 1, 4, back[0].data_ptr(), back[1].data_ptr(), None))
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(back, t0))
+    _lib.check(L.sgfhe_s2_ntt_device(ctx._h, 0, 8, tK[0].data_ptr(), tK[1].data_ptr(), None))
+    out = [torch.zeros((1, 2, S.m), dtype=torch.int64, device="cuda") for _ in mods]
+    _lib.check(L.sgfhe_s2_mac8_device(ctx._h, 1, td[0].data_ptr(), td[1].data_ptr(), tK[0].data_ptr(), tK[1].data_ptr(),
+                                      out[0].data_ptr(), out[1].data_ptr(), None))
+    _lib.check(L.sgfhe_s2_ntt_device(ctx._h, 1, 2, out[0].data_ptr(), out[1].data_ptr(), None))
+    torch.cuda.synchronize()
+    got = [o.cpu().numpy().view(np.uint64) for o in out]
+    for c in range(2):
+        acc = [np.zeros(S.m, object), np.zeros(S.m, object)]
+        for j in range(4):
+            r = so.rns2_polymul(d[0][0, j], d[1][0, j], K[0][0, j, c], K[1][0, j, c], S.B, S.Bp)
+            for l in range(2):
+                acc[l] = (acc[l] + r[l].astype(object)) % mods[l]
+        for l in range(2):
+            assert got[l][0, c].tolist() == acc[l].tolist()
+    ctx.close()
+
+
+@pytest.mark.parametrize("k,rows", [(1, 3), (3, 2)])
+def test_scheme2_bootstrap_key_matches_oracle(so, sg, k, rows):
+    """Scheme2.BootstrapKey (src/fhe2.jl:104-131) generated on the device from pre-drawn a_j, e_j against the oracle"""
+    ctx = sg.Scheme2Context(k)
+    S = ctx.params
+    rng = np.random.default_rng(90 + k)
+    sk = rng.integers(0, 2, size=S.n, dtype=np.uint8)
+    sk[:3] = (1, 0, 1)
+    a = so.rand_below(rng, S.B * S.Bp, (rows, 4, S.m))
+    e = rng.integers(-S.tau, S.tau + 1, size=(rows, 4, S.m), dtype=np.int64)
+    e[0, 0, :2] = (-S.tau, S.tau)
+    got = ctx.bootstrap_key(sk, a, e)
+    assert np.array_equal(got, so.scheme2_bkey_generate(k, sk, a, e, rows))
+    ctx.close()
+
+
+# ---- randomised flatten with draws made on the device (round-1 advisor finding: host draws only fit toy sizes) ---------
+def _philox4x32_10(c, k):
+    """numpy model of the device generator (Salmon et al., SC'11): c uint32[4, N] counters, k uint32[2] key"""
+    c = [x.astype(np.uint64) for x in c]
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & mask]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def _device_draws(sg, P, seed, gate, step0, steps):
+    import ctypes as C
+    from sgfhe_jl_b200 import _lib
+    out = np.zeros((steps, 2, P.m, 2), np.int64)
+    _lib.check(_lib.lib().sgfhe_device_draws(P.ctx, seed, gate, step0, steps, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def test_device_rng_stream_is_philox(sg):
+    """known-answer check of the counter-based generator and of the counter layout (coefficient, 2 step + polynomial, gate),
+    the multiply-shift map onto [-xmax, xmax], and the range / spread of the draws"""
+    kat = _philox4x32_10([np.zeros(1, np.uint32)] * 4, np.zeros(2, np.uint32))
+    assert [int(x[0]) for x in kat] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]       # Random123 kat_vectors, philox4x32-10
+    P = sg.Params(64)
+    seed, gate, step0, steps = 0x1234567890ABCDEF, 77, 3, 2
+    got = _device_draws(sg, P, seed, gate, step0, steps)
+    xmax = P.B // 2 * 3
+    j = np.tile(np.arange(P.m, dtype=np.uint32), steps * 2)
+    sc = np.repeat(np.arange(steps * 2, dtype=np.uint32) + 2 * step0, P.m)                   # 2 step + polynomial
+    r = _philox4x32_10([j, sc, np.full_like(j, gate), np.full_like(j, 0x53474648)],
+                       np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32))
+    for d, (lo, hi) in enumerate(((r[0], r[1]), (r[2], r[3]))):
+        v = [((int(a) | (int(b) << 32)) * (2 * xmax + 1) >> 64) - xmax for a, b in zip(lo, hi)]
+        assert got.reshape(-1, 2)[:, d].tolist() == v
+    assert np.abs(got).max() <= xmax and np.abs(got).max() > 0.99 * xmax and abs(float(got.mean())) < 0.05 * xmax
+    P.close()
+
+
+def test_device_rng_gates_match_oracle_p64(env64, so, sg):
+    """bootstrap with a DeviceRng: every gate equals the oracle's bootstrap run on the draws the device generator makes for
+    that gate (fetched through the seam), successive batches continue the gate counter, and every output decrypts"""
+    P, OP, sk, key, bits, lwes, bkey = env64
+    rng = sg.DeviceRng(20261018)
+    l1, l2 = lwes[:5], lwes[32:37]
+    first = sg.bootstrap_batch(bkey, rng, l1[:2], l2[:2])
+    rest = sg.bootstrap_batch(bkey, rng, l1[2:], l2[2:])             # gates 2..4 of the stream
+    outs = [np.concatenate([a, b]) for a, b in zip(first, rest)]
+    det = sg.bootstrap_batch(bkey, None, l1, l2)
+    assert not np.array_equal(outs[0], det[0])
+    for g in range(5):
+        draws = _device_draws(sg, P, rng.seed, g, 0, OP.n)
+        ref = so.bootstrap(OP, key, l1[g], l2[g], draws)
+        y1, y2 = int(bits[g]), int(bits[32 + g])
+        for o, r_, want in zip(outs, ref, (y1 & y2, y1 | y2, y1 ^ y2)):
+            assert np.array_equal(o[g], r_)
+            assert so.decrypt_lwe(OP, sk, o[g]) == want
+    again = sg.bootstrap_batch(bkey, sg.DeviceRng(20261018), l1, l2)
+    assert all(np.array_equal(a, b) for a, b in zip(outs, again))
+
+
+def test_device_rng_paper_size(env1024, so, sg):
+    """the randomised mode at Params(1024) without host draws: a batch wider than one wave decrypts to the plaintext gates,
+    is reproducible from the seed, and one gate equals the oracle on the device's own draws"""
+    OP, sk, key, bits, lwes = env1024
+    P = sg.Params(1024)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    W = 160
+    l1, l2 = lwes[:W], lwes[W:2 * W]
+    o1 = sg.bootstrap_batch(bkey, sg.DeviceRng(99), l1, l2)
+    o2 = sg.bootstrap_batch(bkey, sg.DeviceRng(99), l1, l2)
+    assert all(np.array_equal(a, b) for a, b in zip(o1, o2))
+    skb = np.asarray(sk, dtype=bool)
+    y1, y2 = bits[:W].astype(np.int64), bits[W:2 * W].astype(np.int64)
+    for a, want in zip(o1, (y1 & y2, y1 | y2, y1 ^ y2)):
+        b1 = (a[:, OP.n].astype(np.int64) - a[:, :OP.n][:, skb].astype(np.int64).sum(axis=1)) % OP.r
+        assert np.array_equal(((b1 + OP.Dr // 2) % OP.r) // OP.Dr, want)
+    g = 151                                                           # a gate of the second wave
+    ref = so.bootstrap_internal(OP, key, l1[g], l2[g], draws=_device_draws(sg, P, 99, g, 0, OP.n), fast=True)
+    for o, r_ in zip(o1, ref):
+        assert o[g].tolist() == [so.rescale(OP.r, v, OP.Q, True) for v in so.unpack(r_)]
+    P.close()

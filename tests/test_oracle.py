@@ -277,3 +277,17 @@ def test_pack_oracle_equals_model(so, gate64):
         oa, ob = so.shortened_external_product(a, key[5], P.B, P.Q, dr)
         ma, mb = md.shortened_external_product(so.unpack(a), so.unpack(key[5]), P.B, P.Q, None if dr is None else dr.tolist())
         assert so.unpack(oa) == ma and so.unpack(ob) == mb
+
+
+def test_rns2_polymul_oracle_vs_model(so):
+    """the oracle's two-limb negacyclic product (Scheme 2, src/fhe2.jl:124 / src/rns.jl:51-52) against the big-integer
+    model's Kronecker product, with the moduli of Scheme2.Params(1) at a short length the model handles quickly"""
+    S = so.scheme2_params(1)
+    N = 256                                           # B - 1 and B' - 1 are divisible by r = 4096, so by 2 N
+    rng = np.random.default_rng(3)
+    a1 = rng.integers(0, S.B, size=N, dtype=np.uint64); a2 = rng.integers(0, S.Bp, size=N, dtype=np.uint64)
+    b1 = rng.integers(0, S.B, size=N, dtype=np.uint64); b2 = rng.integers(0, S.Bp, size=N, dtype=np.uint64)
+    a1[:2] = (S.B - 1, 0); b1[:2] = (S.B - 1, S.B - 1)
+    o1, o2 = so.rns2_polymul(a1, a2, b1, b2, S.B, S.Bp)
+    assert o1.tolist() == md.polymul(a1.tolist(), b1.tolist(), S.B)
+    assert o2.tolist() == md.polymul(a2.tolist(), b2.tolist(), S.Bp)
