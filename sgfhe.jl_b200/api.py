@@ -196,21 +196,23 @@ def decrypt(key: PrivateKey, ct):
 
 
 def _rand_below(rng: np.random.Generator, bound: int, shape) -> np.ndarray:
-    """uniform on [0, bound) as wide uint64[..., 2] (rejection sampling)"""
+    """uniform on [0, bound) as wide uint64[..., 2]: rejection sampling of bit_length(bound)-bit candidates, drawn in bulk
+    (the accepted candidates are used in the order they were drawn)"""
     bits = bound.bit_length()
     n = int(np.prod(shape))
-    out = np.zeros((n, 2), np.uint64)
-    todo = np.arange(n)
+    out = np.empty((n, 2), np.uint64)
     lo_mask = np.uint64((1 << min(bits, 64)) - 1)
-    hi_mask = np.uint64((1 << max(bits - 64, 0)) - 1)
     bh, bl = np.uint64(bound >> 64), np.uint64(bound & 0xFFFFFFFFFFFFFFFF)
-    while todo.size:
-        lo = rng.integers(0, 1 << 64, size=todo.size, dtype=np.uint64) & lo_mask
-        hi = rng.integers(0, 1 << 64, size=todo.size, dtype=np.uint64) & hi_mask
-        ok = (hi < bh) | ((hi == bh) & (lo < bl))
-        out[todo[ok], 0] = lo[ok]
-        out[todo[ok], 1] = hi[ok]
-        todo = todo[~ok]
+    accept = bound / float(1 << bits)
+    filled = 0
+    while filled < n:
+        k = int((n - filled) / accept * 1.05) + 64
+        lo = rng.integers(0, 1 << 64, size=k, dtype=np.uint64) & lo_mask
+        hi = rng.integers(0, 1 << (bits - 64), size=k, dtype=np.uint64) if bits > 64 else np.zeros(k, np.uint64)
+        idx = np.flatnonzero((hi < bh) | ((hi == bh) & (lo < bl)))[: n - filled]
+        out[filled:filled + idx.size, 0] = lo[idx]
+        out[filled:filled + idx.size, 1] = hi[idx]
+        filled += idx.size
     return out.reshape(tuple(shape) + (2,))
 
 
