@@ -57,7 +57,7 @@ def ncu_dram_bytes_per_gate(n: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one bootstrap_kernel launch (ncu --set full capture of a one-wave
     launch at Params(1024), committed under profiles/), per gate; None for other parameter sets."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_r02_traffic.json")) as f:
             t = json.load(f)
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["gates_per_launch"] if n == 1024 else None
     except Exception:
@@ -342,7 +342,7 @@ def run_ours(args) -> None:
             "roofline": {"bound": "int32-pipe", "achieved": per_gpu * imad_gate / 1e9, "peak": peak / 1e9, "unit": "GIMAD/s",
                          "frac": per_gpu * imad_gate / peak,
                          "traffic": (ncu_dram_bytes_per_gate(n) * batch) if ncu_dram_bytes_per_gate(n) else None,
-                         "traffic_note": "ncu DRAM bytes of a 148-gate launch (profiles/ncu_r01_traffic.json) scaled to this batch; "
+                         "traffic_note": "ncu DRAM bytes of a 148-gate launch (profiles/ncu_r02_traffic.json) scaled to this batch; "
                                          "almost all of it is per-gate scratch written back from L2, not algorithmic bytes",
                          "kernel": "bootstrap_kernel (one launch = one step = batch gates x n fused accumulation steps)",
                          "algorithmic_imad_per_gate": imad_gate, "peak_source": peak_src,
