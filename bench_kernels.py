@@ -85,6 +85,44 @@ def main():
                           "modmuls_per_s": 2 * args.count / (ms / 1e3), "ms": ms,
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}}))
 
+    # Scheme 2 (src/fhe2.jl; no reference bootstrap exists): two-limb negacyclic products, transforms and the transform-domain
+    # MAC of an external product at the ring degree of Scheme2.Params(k).  Algorithmic work of a product: 3 transforms of
+    # (m/2) log2 m modmuls + m pointwise, per limb; a 64-bit word modmul counted as a 2-limb Montgomery product (10 IMAD).
+    for k in (1, 2, 3, 4, 5):
+        ctx = sg.Scheme2Context(k)
+        S2, m = ctx.params, ctx.params.m
+        batch = max(64, (args.batch * 8192) // (4 * m))
+        rng = np.random.default_rng(10 + k)
+        mk = lambda M, shape: torch.from_numpy(rng.integers(0, M, size=shape, dtype=np.uint64).view(np.int64)).cuda()
+        a = [mk(S2.B, (batch, m)), mk(S2.Bp, (batch, m))]
+        b = [mk(S2.B, (batch, m)), mk(S2.Bp, (batch, m))]
+        wa, wb = [x.clone() for x in a], [x.clone() for x in b]
+        o = [torch.empty_like(a[0]) for _ in range(2)]
+
+        def product():
+            for w_, src in zip(wa + wb, a + b):
+                w_.copy_(src)                                            # the product overwrites its operands with their transforms
+            _lib.check(L.sgfhe_s2_polymul_device(ctx._h, batch, wa[0].data_ptr(), wa[1].data_ptr(), wb[0].data_ptr(), wb[1].data_ptr(), 0,
+                                                 o[0].data_ptr(), o[1].data_ptr(), stream.cuda_stream))
+        ms_copy = timed(lambda: [w_.copy_(src) for w_, src in zip(wa + wb, a + b)])
+        ms = timed(product) - ms_copy
+        modmuls = 2 * (3 * (m // 2) * (m.bit_length() - 1) + m)
+        rate = batch / (ms / 1e3)
+        print(json.dumps({"kernel": "s2_fwd_top/_local + s2_mulinv_local + s2_inv_top", "workload": f"Scheme2.Params({k}): m={m}, B={S2.B}, Bp={S2.Bp}, batch {batch} products of Polynomial{{RNS2Number}} (no reference bootstrap for this scheme)",
+                          "polymuls_per_s": rate, "ms": ms,
+                          "roofline": {"bound": "int32-pipe", "achieved": rate * modmuls * 10 / 1e9, "peak": imad / 1e9, "unit": "GIMAD/s", "frac": rate * modmuls * 10 / imad},
+                          "hbm_gbs": rate * 2 * 3 * m * 8 / 1e9}))
+        d = [mk(S2.B, (batch, 4, m)), mk(S2.Bp, (batch, 4, m))]
+        K = [mk(S2.B, (batch, 4, 2, m)), mk(S2.Bp, (batch, 4, 2, m))]
+        om = [torch.empty((batch, 2, m), dtype=torch.int64, device="cuda") for _ in range(2)]
+        ms = timed(lambda: _lib.check(L.sgfhe_s2_mac8_device(ctx._h, batch, d[0].data_ptr(), d[1].data_ptr(), K[0].data_ptr(), K[1].data_ptr(),
+                                                            om[0].data_ptr(), om[1].data_ptr(), stream.cuda_stream)))
+        gbs = batch * 2 * (4 + 8 + 2) * m * 8 / (ms / 1e3) / 1e9
+        print(json.dumps({"kernel": "s2_mac8", "workload": f"Scheme2.Params({k}): transform-domain MAC of {batch} external products (4 digit x 4x2 key polynomials, two limbs)",
+                          "external_macs_per_s": batch / (ms / 1e3), "ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}}))
+        ctx.close()
+
 
 if __name__ == "__main__":
     main()

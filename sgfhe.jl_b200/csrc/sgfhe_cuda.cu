@@ -767,9 +767,11 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
       decompose_poly<LOGM, HF>(C, S, 1, d1);
     }
     __syncthreads();
+    uint64_t usum = (A.flags & F_EXT) || k_begin >= k_end ? 0 : l1[k_begin] + l2[k_begin];
     for (int k = k_begin; k < k_end; ++k) {
-      const int u = (A.flags & F_EXT) ? 0 : (int)((l1[k] + l2[k]) & rmask);       // u.a[k], src/fhe.jl:566,580
+      const int u = (int)(usum & rmask);                                          // u.a[k], src/fhe.jl:566,580
       const bool more = k + 1 < k_end;
+      if (more && !(A.flags & F_EXT)) usum = l1[k + 1] + l2[k + 1];               // next step's rotation: in flight during this step
       const uint32_t* keyrow = A.keyhat + (size_t)k * C.L * 8 * m;
       DrawSrc dn = draws_of(k + 1);
       if (!more) { dn.ptr = nullptr; dn.seed = 0; }
