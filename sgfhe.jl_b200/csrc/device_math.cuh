@@ -43,6 +43,7 @@ struct DevConst {
   uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t scale_w1[MAXP], scale_w1_sh[MAXP];   // the same for scale[1] (standalone products)
   uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
+  uint2 topf_h[MAXP][2][7], topi_h[MAXP][2][7];   // v5: per half h of a radix-16 group, the radix-8 after / before its first stage (direct / inverse table entries)
   uint32_t crt_c[2][MAXP][3];               // [1]: (P/p_i) mod Q; [0]: -(P/p_i) mod Q (the bootstrap sums represent -z), 32-bit limbs
   uint32_t negP[2][3];                      // [1]: (-P) mod Q; [0]: (+P) mod Q
   // FP64 head of the v4 bootstrap kernel (head_stage1_f64): p, 1/p, the stage-1 twiddle psi^(m/2), its quotient w/p and

@@ -45,7 +45,7 @@ struct GateArgs {
 
 // acc: the accumulator (a, b) in OFFSET FORM x + offs mod Q (device_math.cuh), limb-major; dig: the biased digit words
 // (dp mod 2^32, dp >> 18) of its gadget decomposition; zres: CRT-ready residues of the two product polynomials.
-struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; double* digd; uint32_t* zres; };
+struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; double* digd; uint32_t* zres; uint32_t* park; uint4* sums; };
 __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   Scratch s;
   s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
@@ -53,6 +53,8 @@ __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   s.dighi = reinterpret_cast<uint32_t*>(base + (size_t)40 * m);       // [4][m]
   s.digd = reinterpret_cast<double*>(base + (size_t)24 * m);          // [4][m] negated digits as doubles (FP64 head; same bytes as diglo + dighi)
   s.zres = reinterpret_cast<uint32_t*>(zbase);                        // [L][2][m]
+  s.park = reinterpret_cast<uint32_t*>(zbase + (size_t)64 * m);       // v5: [4][m/2] forward halves + [2][m/2] inverse halves (zres uses at most 8 * 8 m bytes)
+  s.sums = reinterpret_cast<uint4*>(zbase + (size_t)76 * m);          // v5: [m] unreduced CRT sums
   return s;
 }
 static size_t scratch_bytes(int m) { return (size_t)56 * m; }
@@ -66,7 +68,7 @@ __host__ __device__ __forceinline__ int key_pos(int idx) {
   const int e = idx & 511;
   return (idx & ~511) | (((e >> 2) & 3) << 7) | ((e >> 4) << 2) | (e & 3);
 }
-static size_t zres_bytes(int m, int L) { return (size_t)8 * L * m; }
+static size_t zres_bytes(int m, int L) { (void)L; return (size_t)(64 + 12 + 16) * m; }   // residues (up to 8 primes) + v5 parking + v5 sums
 
 // accumulator init: a = 0, b = t(x) x^(-u_b) DQ   (src/fhe.jl:566-573, t(x) from src/fhe.jl:535-548)
 template <int LOGM>
@@ -136,7 +138,11 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
 //   EXT  (external-product seam): acc = z;   otherwise acc += x^u z - z  (mul_by_xj_minus_one, src/fhe.jl:554-556, applied
 //   to the product), evaluated on the unreduced CRT sums as V = acc + (KQ - S[j]) + (S[j-u] or KQ - S[j-u]) with ONE Barrett
 //   reduction; DEC: fused with the next step's gadget decomposition (RAND: with the caller's draws).
-template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND, bool F64>
+// GSUM: the staged CRT sums are in global memory (v5 kernel): read past L1 (other threads of the CTA wrote them)
+template <bool GSUM>
+__device__ __forceinline__ uint4 ld_sum(const uint4* p) { if (GSUM) return __ldcg(p); return *p; }
+
+template <int LOGM, int T, int D, bool EXT, bool DEC, bool RAND, bool F64, bool GSUM = false>
 __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S, const uint4* sm4, int c,
                                             const DrawSrc draws_next, int u, u96 (&aq)[D]) {
   constexpr int m = 1 << LOGM, KB = 3 * LOGM - 1, SB = 6 * LOGM + 8;
@@ -153,16 +159,16 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
       uint4 V;
       // sm4 holds S' = -z (unreduced, 0 <= S' < KQ): the bootstrap basis' CRT constants are stored negated
       if (EXT) {
-        V = add128(sub128(KQ, sm4[j]), OFF);
+        V = add128(sub128(KQ, ld_sum<GSUM>(sm4 + j)), OFF);
       } else {
         const u96 a = aq[d];
         if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
         const int src = (j - u) & (2 * m - 1);
-        const uint4 nr = sm4[src & (m - 1)];                          // -z[j-u]
+        const uint4 nr = ld_sum<GSUM>(sm4 + (src & (m - 1)));         // -z[j-u]
         const uint4 pr = sub128(KQ, nr);                              // +z[j-u]
         const bool neg = src >= m;                                    // x^u z wraps with a sign flip
         const uint4 zs = make_uint4(neg ? nr.x : pr.x, neg ? nr.y : pr.y, neg ? nr.z : pr.z, neg ? nr.w : pr.w);
-        V = add128(add128(make_uint4(a.x0, a.x1, a.x2, 0), sm4[j]), zs);   // acc - z[j] +- z[j-u]  < Q + 2 KQ < 2^35 Q
+        V = add128(add128(make_uint4(a.x0, a.x1, a.x2, 0), ld_sum<GSUM>(sm4 + j)), zs);   // acc - z[j] +- z[j-u]  < Q + 2 KQ < 2^35 Q
       }
       const u96 res = barrett96<SB>(C, V);
       st96(acc, m, j, res);
@@ -184,14 +190,14 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
 // shared memory, then update_poly.  Every loop reads data written a whole step ago (largely evicted to HBM), so D
 // iterations of loads stay in flight and the first loads of each loop are issued one phase early, across the barriers.
 // OWN: each thread reads only residues it stored itself (v4 kernel), so those loads may precede the entry barrier.
-template <int LOGM, int T, bool OWN, bool F64>
-__device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint32_t* sm,
+template <int LOGM, int T, bool OWN, bool F64, bool GSUM = false>
+__device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, uint4* sm4, uint32_t* stg,
                                            const DrawSrc draws_next, int u, bool ext, bool decompose_next,
                                            unsigned long long* timing, long long& tprev) {
   constexpr int m = 1 << LOGM, L = Shape<LOGM>::L;
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
-  uint4* sm4 = reinterpret_cast<uint4*>(sm);                 // [m] sums: 16 m bytes = the four transform buffers
+  // sm4: [m] unreduced sums, 16 m bytes (the four transform buffers; global scratch in the v5 kernel); stg: staging area
   constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
   uint32_t yq[D][L];
   u96 aq[D];
@@ -205,7 +211,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   // first residues of the SECOND polynomial: async copies into the idle twiddle-table region (behind the accumulator
   // staging), requested now, consumed when the second CRT loop starts
   constexpr bool RS = OWN && (size_t)D * (3 + L) * T * 4 <= (size_t)m * 8;
-  uint32_t* stg_res = sm + 4 * m + D * 3 * T;                // [D][L][T]
+  uint32_t* stg_res = stg + D * 3 * T;                       // [D][L][T]
   if (RS) {
 #pragma unroll
     for (int d = 0; d < D; ++d)
@@ -243,7 +249,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
       }
     }
     constexpr int DS = OWN ? D : 0;                          // accumulator words of the first DS iterations: async copies
-    uint32_t* stg = sm + 4 * m;                              // [DS][3][T] in the (idle) twiddle-table region of the v4 kernel
+    // stg: [DS][3][T] in the (idle) twiddle-table region of the v4 kernel
     if (!ext && DS) {
 #pragma unroll
       for (int d = 0; d < DS; ++d)
@@ -263,13 +269,13 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
       }
     }
     if (ext) {
-      if (!decompose_next) update_poly<LOGM, T, D, true, false, false, F64>(C, S, sm4, c, draws_next, u, aq);
-      else if (draws_next.on()) update_poly<LOGM, T, D, true, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, true, true, false, F64>(C, S, sm4, c, draws_next, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, true, false, false, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
+      else if (draws_next.on()) update_poly<LOGM, T, D, true, true, true, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, true, true, false, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
     } else {
-      if (!decompose_next) update_poly<LOGM, T, D, false, false, false, F64>(C, S, sm4, c, draws_next, u, aq);
-      else if (draws_next.on()) update_poly<LOGM, T, D, false, true, true, F64>(C, S, sm4, c, draws_next, u, aq);
-      else update_poly<LOGM, T, D, false, true, false, F64>(C, S, sm4, c, draws_next, u, aq);
+      if (!decompose_next) update_poly<LOGM, T, D, false, false, false, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
+      else if (draws_next.on()) update_poly<LOGM, T, D, false, true, true, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
+      else update_poly<LOGM, T, D, false, true, false, F64, GSUM>(C, S, sm4, c, draws_next, u, aq);
     }
     __syncthreads();
     SGFHE_TICK(6);
@@ -387,7 +393,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     __syncthreads();
     SGFHE_TICK(4);
   }
-  crt_update<LOGM, T, false, false>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
+  crt_update<LOGM, T, false, false>(C, S, reinterpret_cast<uint4*>(sm), sm + 4 * m, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
 
@@ -706,8 +712,357 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(4);
   }
-  crt_update<LOGM, T, true, HF>(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
+  crt_update<LOGM, T, true, HF>(C, S, reinterpret_cast<uint4*>(sm), sm + 4 * m, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
   if (tid == 0) stage_table(tab, tw_f, m * 8, bar);      // ends with a barrier: the staging area is free again
+#undef SGFHE_TICK
+}
+
+// =========================================================================================================
+// v5: two gates per SM at m = 8192.  One gate per SM (v4) leaves every pipe idle part of the time: the transform phases
+// saturate the FMA-heavy pipe while the CRT / update / decomposition tail is ALU- and latency-bound, and the phases of
+// one gate cannot overlap because each depends on the previous one.  Two independent gates on one SM can.  A gate gets a
+// 256-thread CTA (8 warps, 128 registers per thread) and 81 KiB of shared memory:
+//   * after the top four stages the sixteen 512-point slices of a polynomial are independent, so a prime is processed in
+//     two halves of eight slices (one slice per warp, exactly the per-warp structure of v4): 64 KiB for the four digit
+//     polynomials of a half;
+//   * the head runs the FP64 first stage once per (polynomial, radix-16 group) and parks the eight differences of the second
+//     half in L2 (thread private); the inverse top stages of the first half park their eight outputs the same way and
+//     the second half finishes the last stage against them;
+//   * only twiddles 16..1023 (the two strided passes, 8 KiB per direction) are staged in shared memory by TMA; the
+//     stride-1 level (used once per prime and thread) is read from L2 / L1;
+//   * the unreduced CRT sums of the tail are staged in global scratch instead of shared memory.
+// =========================================================================================================
+struct Shape5 { static constexpr int LOGM = 13, M = 8192, T = 256, HALF = 4096, TABN = 1008; };
+
+// twiddles of one radix-8 block, direct order, from a table that starts at entry `first`
+__device__ __forceinline__ void block_twiddles_at(const uint2* tab, int first, int t1, uint2 (&w)[7]) {
+  w[0] = tab[t1 - first];
+  const uint4 a = *reinterpret_cast<const uint4*>(&tab[2 * t1 - first]);
+  const uint4 b0 = *reinterpret_cast<const uint4*>(&tab[4 * t1 - first]);
+  const uint4 b1 = *reinterpret_cast<const uint4*>(&tab[4 * t1 + 2 - first]);
+  w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
+  w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w); w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
+}
+__device__ __forceinline__ void block_twiddles_ldg(const uint2* __restrict__ tw, int t1, uint2 (&w)[7]) {
+  const uint2 w0 = __ldg(&tw[t1]);
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(&tw[2 * t1]));
+  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1]));
+  const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(&tw[4 * t1 + 2]));
+  w[0] = w0; w[1] = make_uint2(a.x, a.y); w[2] = make_uint2(a.z, a.w);
+  w[3] = make_uint2(b0.x, b0.y); w[4] = make_uint2(b0.z, b0.w); w[5] = make_uint2(b1.x, b1.y); w[6] = make_uint2(b1.z, b1.w);
+}
+
+// one strided radix-8 pass (B = 6 or 3) over NPOLY half polynomials (4096 words each): the warp owns slice 8 h + warp, a lane
+// two adjacent blocks (64-bit shared-memory accesses), twiddles from the staged table of entries 16..1023
+template <int NPOLY, bool FWD, int B>
+__device__ __forceinline__ void pass8_v5(uint32_t* sm, const uint2* tab, int h, uint32_t p, uint32_t z) {
+  const uint32_t p2 = 2 * p;
+  const int blk = ((threadIdx.x >> 5) << 6) | ((threadIdx.x & 31) << 1);
+  const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
+  uint2 w[7];
+  block_twiddles_at(tab, 16, (Shape5::M >> (B + 3)) + ((blk + h * 512) >> B), w);
+  int off[8];
+  if constexpr (B == 6) {
+    const int b0 = swz(base);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = (b0 ^ ((j & 3) << 3)) + (j << 6);
+  } else {
+    const int c = (base >> 6) & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) off[j] = ((base + (((j & 3) ^ c) << 3)) ^ ((j >> 2) << 2)) + ((j >> 2) << 5);
+  }
+#pragma unroll
+  for (int poly = 0; poly < NPOLY; ++poly) {
+    uint32_t* s = sm + poly * Shape5::HALF;
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const uint2 v = *reinterpret_cast<const uint2*>(s + off[j]); x[j] = v.x; y[j] = v.y; }
+    if (FWD) { fwd_block<3>(x, w, p, p2, z); fwd_block<3>(y, w, p, p2, z); }
+    else { inv_block<3>(x, w, p, p2, z); inv_block<3>(y, w, p, p2, z); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint2*>(s + off[j]) = make_uint2(x[j], y[j]);
+  }
+}
+
+// Tail of a v5 step.  96 KiB of shared memory hold (-z) mod Q of one result polynomial as three limb arrays (the unreduced
+// four-limb sums of the v4 tail would need 128 KiB): CRT sum + Barrett per coefficient, barrier, then
+// acc += x^u z - z as acc + r[j] + (r[j-u] or Q - r[j-u]) with two conditional subtractions, fused with the next step's
+// decomposition.  Every thread handles the coefficients tid + 256 it, whose residues, accumulator words and digits are its own.
+template <bool EXT, bool DEC, bool RAND>
+__device__ __forceinline__ void update_v5(const DevConst& C, const Scratch& S, const uint32_t* sm, int c, const DrawSrc draws_next, int u) {
+  constexpr int LOGM = Shape5::LOGM, m = Shape5::M, T = Shape5::T, KB = 3 * LOGM - 1, NIT = m / T, D = 4;
+  const int tid = threadIdx.x;
+  const u96 Q = Q96(C), OFF = off96(C);
+  uint32_t* acc = S.acc + c * 3 * m;
+  u96 aq[D];
+  if (!EXT) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) aq[d] = ld96(acc, m, tid + d * T);
+  }
+#pragma unroll 1
+  for (int it0 = 0; it0 < NIT; it0 += D) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int j = tid + (it0 + d) * T;
+      const u96 rj = ld96(sm, m, j);                                  // (-z[j]) mod Q
+      u96 res;
+      if (EXT) res = addmod96(negmod96(rj, Q), OFF, Q);               // acc = z, in offset form
+      else {
+        const u96 a = aq[d];
+        if (it0 + d + D < NIT) aq[d] = ld96(acc, m, j + D * T);
+        const int src = (j - u) & (2 * m - 1);
+        const u96 rs = ld96(sm, m, src & (m - 1));                    // (-z[j-u]) mod Q
+        uint32_t bw;
+        const u96 pos = sub96(Q, rs, bw);                             // +z[j-u] (= Q when z = 0: absorbed by the csubQ below)
+        const u96 term = sel96(src >= m, rs, pos);                    // x^u z wraps with a sign flip
+        res = csubQ(add96(csubQ(add96(a, rj), Q), term), Q);          // acc - z[j] +- z[j-u]
+      }
+      st96(acc, m, j, res);
+      if (DEC) {
+        uint64_t dp0, dp1;
+        if (RAND) { int64_t x0, x1; get_draws(C, draws_next, c, j, m, x0, x1); decompose_off_rand<KB>(C, res, x0, x1, dp0, dp1); }
+        else decompose_off<KB>(C, res, dp0, dp1);
+        S.digd[(2 * c) * m + j] = digit_f64(dp0); S.digd[(2 * c + 1) * m + j] = digit_f64(dp1);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tail_v5(const DevConst& C, const Scratch& S, uint32_t* sm, const DrawSrc draws_next, int u, bool ext,
+                                        bool decompose_next, unsigned long long* timing, long long& tprev) {
+  constexpr int LOGM = Shape5::LOGM, m = Shape5::M, T = Shape5::T, L = Shape<LOGM>::L, SB = 6 * LOGM + 8, NIT = m / T, D = 4;
+  const int tid = threadIdx.x;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+  uint32_t yq[D][L];
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int i = 0; i < L; ++i) yq[d][i] = S.zres[(size_t)i * 2 * m + tid + d * T];
+  __syncthreads();                                           // every warp has left the transform buffers
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t* zr = S.zres + (size_t)c * m;
+    if (c == 1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + tid + d * T];
+    }
+#pragma unroll 1
+    for (int it0 = 0; it0 < NIT; it0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int idx = tid + (it0 + d) * T;
+        const u96 r = barrett96<SB>(C, crt_sum<0, L>(C, yq[d], 1));
+        if (it0 + d + D < NIT) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) yq[d][i] = zr[(size_t)i * 2 * m + idx + D * T];
+        }
+        st96(sm, m, idx, r);
+      }
+    }
+    __syncthreads();
+    SGFHE_TICK(5);
+    if (ext) {
+      if (!decompose_next) update_v5<true, false, false>(C, S, sm, c, draws_next, u);
+      else if (draws_next.on()) update_v5<true, true, true>(C, S, sm, c, draws_next, u);
+      else update_v5<true, true, false>(C, S, sm, c, draws_next, u);
+    } else {
+      if (!decompose_next) update_v5<false, false, false>(C, S, sm, c, draws_next, u);
+      else if (draws_next.on()) update_v5<false, true, true>(C, S, sm, c, draws_next, u);
+      else update_v5<false, true, false>(C, S, sm, c, draws_next, u);
+    }
+    __syncthreads();
+    SGFHE_TICK(6);
+  }
+#undef SGFHE_TICK
+}
+
+__device__ __forceinline__ void stage_tables_v5(uint2* tabf, uint2* tabi, const uint2* twf, const uint2* twi, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(bar, 2 * Shape5::TABN * 8);
+  bulk_g2s(tabf, twf + 16, Shape5::TABN * 8, bar);
+  bulk_g2s(tabi, twi + 16, Shape5::TABN * 8, bar);
+}
+
+__device__ void gate_step_v5(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
+                             const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i, const DrawSrc draws_next, int u,
+                             bool ext, bool decompose_next, uint2* tabf, uint2* tabi, uint64_t* bar, uint32_t& parity,
+                             unsigned long long* timing) {
+  constexpr int LOGM = Shape5::LOGM, m = Shape5::M, T = Shape5::T, HALF = Shape5::HALF, L = Shape<LOGM>::L;
+  const int tid = threadIdx.x;
+  long long tprev = timing ? clock64() : 0;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+  const int st = swz(tid);                               // swz(tid + 256 q + 512 k) = swz(tid) + 256 q + 512 k
+  const int blk0 = ((tid >> 5) << 6) | ((tid & 31) << 1);     // the lane's first (even) radix-8 block inside the half
+  double dd[2][16];
+  auto load_digits = [&](const int b, const int item) {  // item = 2 poly + group: the 16 digits t + 512 k of radix-16 group t
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dd[b][k] = S.digd[(item >> 1) * m + tid + (item & 1) * T + k * 512];
+  };
+  load_digits(0, 0);
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {
+    const uint32_t p = C.p[i], p2 = 2 * p, z = C.zero;
+    const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
+    const uint2* twf = tw_f + (size_t)i * m;
+    const uint2* twi = tw_i + (size_t)i * m;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      // ---- head of this half: (h = 0) digits -> FP64 first stage -> sums go on, differences are parked;
+      //      (h = 1) the parked differences come back.  Then three stages in registers -> shared memory. ----
+      if (h == 0) {
+        const double fp = C.hp_p[i], fpinv = C.hp_pinv[i], fw = C.hp_w[i], fwp = C.hp_wp[i], fc = C.hp_c[i];
+#pragma unroll
+        for (int item = 0; item < 8; ++item) {
+          if (item + 1 < 8) load_digits((item + 1) & 1, item + 1);
+          uint32_t x[16];
+          head_stage1_f64<16>(dd[item & 1], x, fp, fpinv, fw, fwp, fc);
+          uint32_t* pk = S.park + (size_t)item * 8 * T + tid;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pk[k * T] = x[8 + k];
+          uint32_t lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lo[k] = x[k];
+          fwd_block<3>(lo, C.topf_h[i][0], p, p2, z);
+          uint32_t* dst = sm + (item >> 1) * HALF + st + (item & 1) * T;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k * 512] = lo[k];
+        }
+      } else {
+        uint32_t pv[2][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pv[0][k] = S.park[(size_t)k * T + tid];
+#pragma unroll
+        for (int item = 0; item < 8; ++item) {
+          if (item + 1 < 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pv[(item + 1) & 1][k] = S.park[((size_t)(item + 1) * 8 + k) * T + tid];
+          }
+          uint32_t x[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = pv[item & 1][k];
+          fwd_block<3>(x, C.topf_h[i][1], p, p2, z);
+          uint32_t* dst = sm + (item >> 1) * HALF + st + (item & 1) * T;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dst[k * 512] = x[k];
+        }
+      }
+      __syncthreads();
+      if (h == 0) { mbar_wait(bar, parity); parity ^= 1; }      // tables of this prime (staged one prime ago)
+      SGFHE_TICK(0);
+      pass8_v5<4, true, 6>(sm, tabf, h, p, z);
+      __syncwarp();                                      // a warp owns its slice: bits [0,9) never leave it
+      uint4 kq[2][4];
+      {
+        const int pt = 8 * (blk0 + h * 512);
+        const int kb = key_pos<LOGM>(pt), kh = key_pos<LOGM>(pt + 4);
+        kq[0][0] = __ldg(reinterpret_cast<const uint4*>(K + kb)); kq[0][1] = __ldg(reinterpret_cast<const uint4*>(K + kh));
+        kq[0][2] = __ldg(reinterpret_cast<const uint4*>(K + m + kb)); kq[0][3] = __ldg(reinterpret_cast<const uint4*>(K + m + kh));
+      }
+      uint2 wnext[7];                                    // stride-1 twiddles come from L2: requested one block phase ahead
+      block_twiddles_ldg(twf, m / 8 + blk0 + h * 512, wnext);
+      pass8_v5<4, true, 3>(sm, tabf, h, p, z);
+      __syncwarp();
+      SGFHE_TICK(1);
+      // ---- fused: stride-1 forward pass + 8 key MACs per point + stride-1 inverse pass ----
+      {
+        const uint32_t pinv = C.pinv_neg[i];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int blk = blk0 + q, base = 8 * blk, blkg = blk + h * 512;
+          const int a0 = swz(base), a1 = a0 ^ 4;
+          uint2 w[7], wi[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) w[k] = wnext[k];
+          block_twiddles_ldg(twi, m / 8 + blkg, wi);      // inverse twiddles of this block: in flight under the forward part
+          uint64_t sa[8], sb[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sa[e] = 0; sb[e] = 0; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int sidx = q * 4 + j;
+            if (sidx + 1 < 8) {                            // prefetch the next (block, poly) key words
+              const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
+              const int pt = 8 * (blk0 + nq + h * 512);
+              const int kb = key_pos<LOGM>(pt), kh = key_pos<LOGM>(pt + 4);
+              const uint32_t* r0 = K + (size_t)(2 * nj) * m;
+              const uint32_t* r1 = K + (size_t)(2 * nj + 1) * m;
+              kq[(sidx + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(r0 + kb)); kq[(sidx + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(r0 + kh));
+              kq[(sidx + 1) & 1][2] = __ldg(reinterpret_cast<const uint4*>(r1 + kb)); kq[(sidx + 1) & 1][3] = __ldg(reinterpret_cast<const uint4*>(r1 + kh));
+            }
+            uint32_t x[8];
+            {
+              const uint4 v0 = *reinterpret_cast<const uint4*>(sm + j * HALF + a0);
+              const uint4 v1 = *reinterpret_cast<const uint4*>(sm + j * HALF + a1);
+              x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            }
+            fwd_block<3>(x, w, p, p2, z);
+            const uint4* kk = kq[sidx & 1];
+            const uint32_t ka[8] = {kk[0].x, kk[0].y, kk[0].z, kk[0].w, kk[1].x, kk[1].y, kk[1].z, kk[1].w};
+            const uint32_t kb[8] = {kk[2].x, kk[2].y, kk[2].z, kk[2].w, kk[3].x, kk[3].y, kk[3].z, kk[3].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t d = min(x[e], x[e] - p2);                 // [0, 2p): four products < 8 p^2 < 2^63
+              sa[e] += (uint64_t)d * ka[e];
+              sb[e] += (uint64_t)d * kb[e];
+            }
+          }
+          if (q == 0) block_twiddles_ldg(twf, m / 8 + blkg + 1, wnext);
+          uint32_t ya[8], yb[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {                                // redc of T < 8 p^2 lands in [0, 3p)
+            ya[e] = redc(sa[e], p, pinv); ya[e] = min(ya[e], ya[e] - p2);
+            yb[e] = redc(sb[e], p, pinv); yb[e] = min(yb[e], yb[e] - p2);
+          }
+          inv_block<3>(ya, wi, p, p2, z);
+          inv_block<3>(yb, wi, p, p2, z);
+          *reinterpret_cast<uint4*>(sm + a0) = make_uint4(ya[0], ya[1], ya[2], ya[3]);
+          *reinterpret_cast<uint4*>(sm + a1) = make_uint4(ya[4], ya[5], ya[6], ya[7]);
+          *reinterpret_cast<uint4*>(sm + HALF + a0) = make_uint4(yb[0], yb[1], yb[2], yb[3]);
+          *reinterpret_cast<uint4*>(sm + HALF + a1) = make_uint4(yb[4], yb[5], yb[6], yb[7]);
+        }
+      }
+      __syncwarp();
+      SGFHE_TICK(2);
+      pass8_v5<2, false, 3>(sm, tabi, h, p, z);
+      __syncwarp();
+      pass8_v5<2, false, 6>(sm, tabi, h, p, z);
+      if (h == 1 && i + 1 < L) load_digits(0, 0);        // next prime's first digits: in flight across the barrier
+      __syncthreads();
+      if (h == 1 && tid == 0) {                          // last reader of the tables is done: next prime's (or next step's prime 0)
+        const int nx = i + 1 < L ? i + 1 : 0;
+        stage_tables_v5(tabf, tabi, tw_f + (size_t)nx * m, tw_i + (size_t)nx * m, bar);
+      }
+      SGFHE_TICK(3);
+      // ---- inverse top stages of this half in registers; the last stage joins the two halves ----
+      {
+        const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i], sw = C.scale_w[i], sws = C.scale_w_sh[i];
+#pragma unroll
+        for (int item = 0; item < 4; ++item) {             // item = 2 c + group
+          const int c = item >> 1, t = tid + (item & 1) * T;
+          uint32_t x[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = sm[c * HALF + st + (item & 1) * T + k * 512];
+          inv_block<3>(x, C.topi_h[i][h], p, p2, z);
+          uint32_t* pk = sm + 4 * HALF + item * 8 * T + tid;   // thread-private words behind the four half buffers
+          if (h == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pk[k * T] = x[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t y0 = pk[k * T];               // first half's value of the pair (k, k + 8)
+              const uint32_t s0 = y0 + x[k] + z, d0 = y0 - x[k] + p2;
+              S.zres[((size_t)i * 2 + c) * m + t + k * 512] = csub(shoup_mul(s0, sc, scs, p), p);
+              S.zres[((size_t)i * 2 + c) * m + t + (k + 8) * 512] = csub(shoup_mul(d0, sw, sws, p), p);
+            }
+          }
+        }
+      }
+      SGFHE_TICK(4);
+    }
+  }
+  tail_v5(C, S, sm, draws_next, u, ext, decompose_next, timing, tprev);
 #undef SGFHE_TICK
 }
 
@@ -716,9 +1071,9 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 // takes the next unprocessed gate when it finishes one instead of a fixed share of the batch.
 // F_DECOMP: (re)compute S.dig from S.acc before the first step of this launch (set with F_INIT, and by the
 // trace / external-product seams whose accumulator arrives from a previous launch or from the host).
-template <int LOGM, bool V4, bool HF>
+template <int LOGM, int VER, bool HF>
 __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, uint32_t* sm, uint2* tab, uint64_t* bar,
-                                          uint32_t& parity) {
+                                          uint32_t& parity, uint32_t* slot) {
   constexpr int m = 1 << LOGM;
   const int n = C.n;
   const Scratch S = carve(A.scratch + (size_t)blockIdx.x * A.scratch_stride, A.zres + (size_t)blockIdx.x * A.zres_stride, m);
@@ -729,9 +1084,9 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
   }
   for (int g = blockIdx.x;;) {
     if (A.work_counter) {
-      if (threadIdx.x == 0) sm[6 * m + 2] = (uint32_t)atomicAdd(A.work_counter, 1);
+      if (threadIdx.x == 0) *slot = (uint32_t)atomicAdd(A.work_counter, 1);
       __syncthreads();
-      g = (int)sm[6 * m + 2];
+      g = (int)*slot;
     }
     if (g >= A.batch) break;
     const uint64_t* l1 = A.lwe1 + (size_t)g * (n + 1);
@@ -776,7 +1131,8 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
       DrawSrc dn = draws_of(k + 1);
       if (!more) { dn.ptr = nullptr; dn.seed = 0; }
       unsigned long long* tm = blockIdx.x == 0 ? A.timing : nullptr;
-      if constexpr (V4) gate_step_v4<LOGM, HF>(C, S, sm, keyrow, A.tw_f, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
+      if constexpr (VER == 5) gate_step_v5(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, tab + Shape5::TABN, bar, parity, tm);
+      else if constexpr (VER == 4) gate_step_v4<LOGM, HF>(C, S, sm, keyrow, A.tw_f, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
       else gate_step<LOGM>(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
     }
     if (A.trace) {
@@ -806,7 +1162,7 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
   uint32_t parity = 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  run_gates<LOGM, false, false>(C, A, sm, tab, bar, parity);
+  run_gates<LOGM, 3, false>(C, A, sm, tab, bar, parity, sm + 6 * m + 2);
 }
 
 template <int LOGM, bool HF>
@@ -822,9 +1178,32 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
     stage_table(tab, A.tw_f, m * 8, bar);
   }
   __syncthreads();
-  run_gates<LOGM, true, HF>(C, A, sm, tab, bar, parity);
+  run_gates<LOGM, 4, HF>(C, A, sm, tab, bar, parity, sm + 6 * m + 2);
   mbar_wait(bar, parity);                                // the table staged for a step that never runs
 }
+
+// two CTAs (gates) per SM; the CTAs of the second wave start half a step late so that the two gates of an SM are in
+// different phases from the start
+__global__ void __launch_bounds__(Shape5::T, 2)
+bootstrap_kernel_v5(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint2* tabf = reinterpret_cast<uint2*>(sm + 6 * Shape5::HALF);    // 96 KiB: four half buffers + inverse parking; three limb arrays in the tail
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tabf + 2 * Shape5::TABN);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    stage_tables_v5(tabf, tabf + Shape5::TABN, A.tw_f, A.tw_i, bar);
+  }
+  __syncthreads();
+  if (2 * blockIdx.x >= gridDim.x && A.stagger_cycles >= 0) {
+    const long long t0 = clock64(), wait = A.stagger_cycles > 0 ? A.stagger_cycles : 100000;
+    while (clock64() - t0 < wait) __nanosleep(1024);
+  }
+  GateArgs B = A; B.stagger_cycles = 0;
+  run_gates<Shape5::LOGM, 5, true>(C, B, sm, tabf, bar, parity, reinterpret_cast<uint32_t*>(bar + 1));
+  mbar_wait(bar, parity);                                // the tables staged for a step that never runs
+}
+static constexpr size_t kSmemV5 = (size_t)6 * Shape5::HALF * 4 + (size_t)2 * Shape5::TABN * 8 + 32;
 
 // Key pre-transform (K10): coefficient-form wide polys -> per-prime NTT domain, Montgomery form.
 // grid = (npolys, L).  coef: [npolys][m][2];  out: poly P of row k=P/8, slot jc=P%8 -> keyhat[((k L + i) 8 + jc) m ..]
@@ -1264,9 +1643,10 @@ struct sgfhe_ctx {
   int device = 0;
   HostParams hp;
   DevConst dc;
-  int num_sms = 0, threads = 0, boot_threads = 0, max_ctas = 0;
+  int num_sms = 0, threads = 0, boot_threads = 0, boot_threads_gate = 0, max_ctas = 0;
   bool use_v4 = false;
   bool head_f64 = true;                            // v4 gate kernel: digits as doubles, first forward stage on the FP64 pipe
+  bool use_v5 = false;                             // m = 8192: two gates per SM (bootstrap_kernel_v5)
   size_t smem_bytes = 0, scratch_stride = 0, zres_stride = 0;
   int persist_l2 = 0;                              // pin accumulator + digit scratch in L2 (access policy window)
   uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
@@ -1392,6 +1772,10 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       dc->topf[i][k - 1] = f;
       dc->topi[i][k - 1] = make_uint2((uint32_t)p - mir.x, ~mir.y);
     }
+    for (int h = 0; h < 2 && hp.logm >= 12; ++h) {       // v5: the radix-8 that follows the first stage inside half h of a radix-16 group
+      const int idx[7] = {2 + h, 4 + 2 * h, 5 + 2 * h, 8 + 4 * h, 9 + 4 * h, 10 + 4 * h, 11 + 4 * h};
+      for (int k = 0; k < 7; ++k) { dc->topf_h[i][h][k] = (*twf)[(size_t)i * m + idx[k]]; dc->topi_h[i][h][k] = (*twi)[(size_t)i * m + idx[k]]; }
+    }
     dc->hp_w[i] = (double)(*twf)[(size_t)i * m + 1].x;                       // stage-1 twiddle psi^(m/2)
     dc->hp_wp[i] = dc->hp_w[i] / (double)p;
   }
@@ -1419,6 +1803,10 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   cudaError_t e = cudaSuccess;
   c->use_v4 = c->hp.logm >= 12 && !getenv("SGFHE_FORCE_V3");
   c->head_f64 = !getenv("SGFHE_HEAD_INT");           // A/B knob: the all-integer head of round 1
+  // experimental, off by default: two gates per SM.  Measured slower than v4 (231 k against 201 k cycles per gate-step): 296
+  // gates in flight double the scratch working set to 246 MB, the L2 hit rate falls from 78 % to 48 % and the DRAM traffic per
+  // gate rises from 1.0 to 2.5 GB (profiles/ncu_r02_v5_summary.txt); kept selectable for that comparison and parity-tested
+  c->use_v5 = c->use_v4 && c->hp.logm == 13 && c->head_f64 && getenv("SGFHE_V5");
   if (c->use_v4) {
     SGFHE_DISPATCH_V4(c->hp.logm, {
       c->boot_threads = Shape4<LOGM_>::T;
@@ -1428,6 +1816,12 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads, c->smem_bytes);
     });
     if (e != cudaSuccess) return e;
+    if (c->use_v5) {
+      e = cudaFuncSetAttribute(bootstrap_kernel_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemV5);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v5, Shape5::T, kSmemV5);
+      if (e != cudaSuccess) return e;
+      c->boot_threads_gate = Shape5::T;
+    }
   }
   SGFHE_DISPATCH(c->hp.logm, {
     c->threads = Shape<LOGM_>::T;
@@ -1440,6 +1834,11 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   return e;
 }
 static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, const GateArgs& A) {
+  if (c->use_v5) {
+    bootstrap_kernel_v5<<<grid, Shape5::T, kSmemV5, st>>>(c->dc, A);
+    ++g_launches;
+    return;
+  }
   if (c->use_v4) {
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;

@@ -833,3 +833,27 @@ def test_device_rng_paper_size(env1024, so, sg):
     for o, r_ in zip(o1, ref):
         assert o[g].tolist() == [so.rescale(OP.r, v, OP.Q, True) for v in so.unpack(r_)]
     P.close()
+
+
+def test_two_gates_per_sm_variant_p1024(env1024, so, sg, monkeypatch):
+    """bootstrap_kernel_v5 (experimental, SGFHE_V5=1: 256-thread CTAs, two gates per SM, half the slices at a time) gives
+    the default kernel's ciphertexts bit for bit, over more gates than resident CTAs, and the oracle's accumulators"""
+    OP, sk, key, bits, lwes = env1024
+    P4 = sg.Params(1024)
+    k4 = sg.BootstrapKey(params=P4, key=key)
+    W = 310
+    l1, l2 = lwes[:W], lwes[W:2 * W]
+    ref = sg.bootstrap_batch(k4, None, l1, l2)
+    P4.close()
+    monkeypatch.setenv("SGFHE_V5", "1")
+    P5 = sg.Params(1024)
+    k5 = sg.BootstrapKey(params=P5, key=key)
+    got = sg.bootstrap_batch(k5, None, l1, l2)
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    rng = np.random.default_rng(8)
+    xmax = OP.B // 2 * 3
+    for draws in (None, rng.integers(-xmax, xmax + 1, size=(3, 2, OP.m, 2), dtype=np.int64)):
+        ga, go, gx, gtr = sg.bootstrap_trace(k5, draws, lwes[3], lwes[700], n_steps=3)
+        ra, ro, rx, rtr = so.bootstrap_internal(OP, key[:3], lwes[3], lwes[700], draws=draws, n_steps=3, trace=True, fast=True)
+        assert np.array_equal(gtr, rtr) and np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
+    P5.close()
