@@ -487,7 +487,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--n", "--params-n", dest="n", type=int, default=1024,
+                    help="Params(n); under torchrun spell it --params-n (torchrun's own parser finds a bare --n ambiguous)")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
