@@ -96,25 +96,83 @@ __global__ void s2_inv_top(uint64_t* __restrict__ data, PrimeC P, int logm, size
   for (int k = 0; k < (1 << T); ++k) d[(size_t)k << (logm - T)] = csub64(shoup64(x[k], P.minv, P.p), P.p);
 }
 
-// stages s0 .. logm-1 of the forward transform on the block `blk` (of 2^s0) of a polynomial held in shared memory
-__device__ void local_fwd(uint64_t* sm, int logm, int s0, int blk, PrimeC P) {
-  const int nloc = 1 << (logm - s0);
-  for (int s = s0; s < logm; ++s) {
-    const int half = 1 << (logm - s - 1);
-    for (int t = threadIdx.x; t < nloc / 2; t += blockDim.x) {
-      const int b = t / half, j = t % half, i0 = b * 2 * half + j;
-      ct64(sm[i0], sm[i0 + half], P.twf[((size_t)1 << s) + ((size_t)blk << (s - s0)) + b], P.p);
+// 64-bit words in shared memory: 16 banks of 8 bytes.  XOR-ing index bits 4..6 into bits 0..2 keeps the radix-8 passes with
+// strides 1, 64 and 512 conflict free and the stride-8 pass two-way.
+__device__ __forceinline__ int swz64(int i) { return i ^ ((i >> 4) & 7); }
+
+// radix-2^LOGR register block over elements base + j 2^B of the local array; twiddle of group g at level l is
+// tw[(t1 << l) + g] with t1 = 2^s + (global block index of the first level), s the stage of that level
+template <int LOGR, bool FWD>
+__device__ __forceinline__ void local_pass(uint64_t* sm, int B, int t, const Tw64* tw, size_t t1, uint64_t p) {
+  constexpr int R = 1 << LOGR;
+  const int base = ((t >> B) << (B + LOGR)) | (t & ((1 << B) - 1));
+  uint64_t x[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) x[j] = sm[swz64(base + (j << B))];
+  if (FWD) {
+#pragma unroll
+    for (int l = 0; l < LOGR; ++l) {
+      const int half = R >> (l + 1);
+#pragma unroll
+      for (int g = 0; g < (1 << l); ++g) {
+        const Tw64 w = tw[(t1 << l) + g];
+#pragma unroll
+        for (int k = 0; k < half; ++k) ct64(x[g * 2 * half + k], x[g * 2 * half + k + half], w, p);
+      }
     }
+  } else {
+#pragma unroll
+    for (int l = LOGR - 1; l >= 0; --l) {
+      const int half = R >> (l + 1);
+#pragma unroll
+      for (int g = 0; g < (1 << l); ++g) {
+        const Tw64 w = tw[(t1 << l) + g];
+#pragma unroll
+        for (int k = 0; k < half; ++k) gs64(x[g * 2 * half + k], x[g * 2 * half + k + half], w, p);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) sm[swz64(base + (j << B))] = x[j];
+}
+
+// stages s0 .. logm-1 of the forward transform on block `blk` (of 2^s0) of a polynomial held (swizzled) in shared memory:
+// the (logm - s0) % 3 top stages as one small pass, then radix-8 passes from the high bits down
+__device__ void local_fwd(uint64_t* sm, int logm, int s0, int blk, PrimeC P) {
+  const int ll = logm - s0, rem = ll % 3;
+  int s = s0, B = ll;                                    // next stage, bits [0, B) still to do
+  if (rem) {
+    B -= rem;
+    for (int t = threadIdx.x; t < (1 << (ll - rem)); t += blockDim.x) {
+      const size_t t1 = ((size_t)1 << s) + ((size_t)blk << (s - s0)) + (t >> B);
+      if (rem == 1) local_pass<1, true>(sm, B, t, P.twf, t1, P.p); else local_pass<2, true>(sm, B, t, P.twf, t1, P.p);
+    }
+    s += rem;
+    __syncthreads();
+  }
+  while (B > 0) {
+    B -= 3;
+    for (int t = threadIdx.x; t < (1 << (ll - 3)); t += blockDim.x)
+      local_pass<3, true>(sm, B, t, P.twf, ((size_t)1 << s) + ((size_t)blk << (s - s0)) + (t >> B), P.p);
+    s += 3;
     __syncthreads();
   }
 }
 __device__ void local_inv(uint64_t* sm, int logm, int s0, int blk, PrimeC P) {
-  const int nloc = 1 << (logm - s0);
-  for (int s = logm - 1; s >= s0; --s) {
-    const int half = 1 << (logm - s - 1);
-    for (int t = threadIdx.x; t < nloc / 2; t += blockDim.x) {
-      const int b = t / half, j = t % half, i0 = b * 2 * half + j;
-      gs64(sm[i0], sm[i0 + half], P.twi[((size_t)1 << s) + ((size_t)blk << (s - s0)) + b], P.p);
+  const int ll = logm - s0, rem = ll % 3;
+  int s = logm, B = 0;                                   // stages [s, logm) are undone, bits [0, B) are done
+  while (B + 3 <= ll - rem) {
+    s -= 3;
+    for (int t = threadIdx.x; t < (1 << (ll - 3)); t += blockDim.x)
+      local_pass<3, false>(sm, B, t, P.twi, ((size_t)1 << s) + ((size_t)blk << (s - s0)) + (t >> B), P.p);
+    B += 3;
+    __syncthreads();
+  }
+  if (rem) {
+    s -= rem;
+    for (int t = threadIdx.x; t < (1 << (ll - rem)); t += blockDim.x) {
+      const size_t t1 = ((size_t)1 << s) + ((size_t)blk << (s - s0)) + (t >> B);
+      if (rem == 1) local_pass<1, false>(sm, B, t, P.twi, t1, P.p); else local_pass<2, false>(sm, B, t, P.twi, t1, P.p);
     }
     __syncthreads();
   }
@@ -125,10 +183,10 @@ __global__ void s2_fwd_local(uint64_t* __restrict__ data, PrimeC P, int logm, in
   extern __shared__ __align__(16) uint64_t sm64[];
   const int nloc = 1 << (logm - s0), blk = blockIdx.x & ((1 << s0) - 1);
   uint64_t* d = data + (size_t)blockIdx.x * nloc;                      // blocks of one polynomial are consecutive
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[i] = d[i];
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[swz64(i)] = d[i];
   __syncthreads();
   local_fwd(sm64, logm, s0, blk, P);
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) { uint64_t v = sm64[i]; v = v >= 2 * P.p ? v - 2 * P.p : v; d[i] = csub64(v, P.p); }
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) { uint64_t v = sm64[swz64(i)]; v = v >= 2 * P.p ? v - 2 * P.p : v; d[i] = csub64(v, P.p); }
 }
 
 // pointwise product of two transformed polynomials (b broadcast when b_stride == 0) + inverse stages logm-1 .. s0;
@@ -139,11 +197,11 @@ __global__ void s2_mulinv_local(const uint64_t* ah, const uint64_t* bh, size_t b
   const int nloc = 1 << (logm - s0), blk = blockIdx.x & ((1 << s0) - 1);
   const size_t poly = blockIdx.x >> s0, off = (size_t)blockIdx.x * nloc;
   const uint64_t* b = bh + poly * b_stride + (size_t)blk * nloc;
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[i] = mulmod48(ah[off + i], b[i], P.p, P.mu);
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[swz64(i)] = mulmod48(ah[off + i], b[i], P.p, P.mu);
   __syncthreads();
   local_inv(sm64, logm, s0, blk, P);
   for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-    uint64_t v = sm64[i];
+    uint64_t v = sm64[swz64(i)];
     if (s0 == 0) v = csub64(shoup64(v, P.minv, P.p), P.p);
     out[off + i] = v;                                                  // [0, 2p) when s2_inv_top follows
   }
@@ -154,11 +212,11 @@ __global__ void s2_inv_local(uint64_t* __restrict__ data, PrimeC P, int logm, in
   extern __shared__ __align__(16) uint64_t sm64[];
   const int nloc = 1 << (logm - s0), blk = blockIdx.x & ((1 << s0) - 1);
   uint64_t* d = data + (size_t)blockIdx.x * nloc;
-  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[i] = d[i];
+  for (int i = threadIdx.x; i < nloc; i += blockDim.x) sm64[swz64(i)] = d[i];
   __syncthreads();
   local_inv(sm64, logm, s0, blk, P);
   for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-    uint64_t v = sm64[i];
+    uint64_t v = sm64[swz64(i)];
     if (s0 == 0) v = csub64(shoup64(v, P.minv, P.p), P.p);
     d[i] = v;
   }

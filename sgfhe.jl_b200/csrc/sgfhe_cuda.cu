@@ -2202,7 +2202,7 @@ extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t
     c->io_capacity = 5 * lwe_bytes;
   }
   uint64_t* d_io = c->d_io; int64_t* d_draws = nullptr;
-  if (draws && cudaMalloc(&d_draws, draw_bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc of draws failed");
+  if (draws) { const int rca = ensure_arena(c, draw_bytes); if (rca) return rca; d_draws = reinterpret_cast<int64_t*>(c->d_arena); }
   const size_t w = lwe_bytes / sizeof(uint64_t);
   int rc = SGFHE_OK;
   cudaError_t e = cudaMemcpyAsync(d_io, lwe1, lwe_bytes, cudaMemcpyHostToDevice, nullptr);
@@ -2214,7 +2214,6 @@ extern "C" int sgfhe_bootstrap_batch(sgfhe_ctx* c, int32_t batch, const uint64_t
   if (rc == SGFHE_OK && e == cudaSuccess) e = cudaMemcpyAsync(out_xor, d_io + 4 * w, lwe_bytes, cudaMemcpyDeviceToHost, nullptr);
   const cudaError_t es = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = es;
-  cudaFree(d_draws);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("bootstrap_batch: ") + cudaGetErrorString(e));
   return SGFHE_OK;
@@ -2493,14 +2492,12 @@ extern "C" int sgfhe_split_ciphertext(sgfhe_ctx* c, int32_t count, int32_t N, co
   if (count == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
   const size_t in_w = (size_t)count * N, out_w = (size_t)count * c->hp.n * (c->hp.n + 1);
-  uint64_t* d = nullptr;
-  if (cudaMalloc(&d, (2 * in_w + out_w) * 8) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
-  cudaError_t e = cudaMemcpy(d, a, in_w * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d + in_w, b, in_w * 8, cudaMemcpyHostToDevice);
-  int rc = SGFHE_OK;
+  int rc = ensure_arena(c, (2 * in_w + out_w) * 8); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
+  cudaError_t e = cudaMemcpyAsync(d, a, in_w * 8, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + in_w, b, in_w * 8, cudaMemcpyHostToDevice, nullptr);
   if (e == cudaSuccess) rc = sgfhe_split_ciphertext_device(c, count, N, d, d + in_w, d + 2 * in_w, nullptr);
   if (!rc && e == cudaSuccess) e = cudaMemcpy(lwes, d + 2 * in_w, out_w * 8, cudaMemcpyDeviceToHost);
-  cudaFree(d);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("split_ciphertext: ") + cudaGetErrorString(e));
   return SGFHE_OK;
@@ -2525,14 +2522,12 @@ extern "C" int sgfhe_decrypt_bits(sgfhe_ctx* c, int32_t count, const uint64_t* l
   if (count == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
   const size_t lw = (size_t)count * (c->hp.n + 1) * 8;
-  uint8_t* d = nullptr;
-  if (cudaMalloc(&d, lw + c->hp.n + count) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
-  cudaError_t e = cudaMemcpy(d, lwes, lw, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d + lw, sk, c->hp.n, cudaMemcpyHostToDevice);
-  int rc = SGFHE_OK;
+  int rc = ensure_arena(c, lw + c->hp.n + count); if (rc) return rc;
+  uint8_t* d = c->d_arena;
+  cudaError_t e = cudaMemcpyAsync(d, lwes, lw, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + lw, sk, c->hp.n, cudaMemcpyHostToDevice, nullptr);
   if (e == cudaSuccess) rc = sgfhe_decrypt_bits_device(c, count, reinterpret_cast<uint64_t*>(d), d + lw, d + lw + c->hp.n, nullptr);
   if (!rc && e == cudaSuccess) e = cudaMemcpy(out, d + lw + c->hp.n, count, cudaMemcpyDeviceToHost);
-  cudaFree(d);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("decrypt_bits: ") + cudaGetErrorString(e));
   return SGFHE_OK;
@@ -2625,15 +2620,13 @@ extern "C" int sgfhe_polymul(sgfhe_ctx* c, int32_t batch, const uint64_t* a, con
   if (batch == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
   const size_t bytes = (size_t)batch * c->hp.m * 16;
-  uint64_t* d = nullptr;
-  if (cudaMalloc(&d, 3 * bytes) != cudaSuccess) return fail(SGFHE_ERR_NOMEM, "cudaMalloc failed");
+  int rc = ensure_arena(c, 3 * bytes); if (rc) return rc;
+  uint64_t* d = reinterpret_cast<uint64_t*>(c->d_arena);
   uint64_t* da = d; uint64_t* db = d + bytes / 8; uint64_t* dout = d + 2 * (bytes / 8);
-  int rc = SGFHE_OK;
-  cudaError_t e = cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) { rc = sgfhe_polymul_device(c, batch, da, db, dout, nullptr); if (!rc) e = cudaDeviceSynchronize(); }
+  cudaError_t e = cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, nullptr);
+  if (e == cudaSuccess) rc = sgfhe_polymul_device(c, batch, da, db, dout, nullptr);
   if (!rc && e == cudaSuccess) e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
-  cudaFree(d);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(SGFHE_ERR_CUDA, std::string("polymul: ") + cudaGetErrorString(e));
   return SGFHE_OK;
