@@ -433,7 +433,9 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
 //   * at m = 8192 every warp owns one 512-point slice between the top stages (warp-level synchronisation only), a lane
 //     works on two adjacent radix-8 blocks (64-bit shared-memory accesses);
 //   * the CRT sums stay unreduced until the accumulator update (one Barrett step per coefficient, FP64-assisted), the first
-//     loads of the tail arrive by cp.async in the then idle twiddle-table region.
+//     loads of the tail arrive by cp.async in the then idle twiddle-table region;
+//   * HF (round 2, the default): the digits are stored as doubles and the digit reduction plus the first forward stage run
+//     on the FP64 pipe (head_stage1_f64), which the integer kernel left idle.
 // =========================================================================================================
 template <int LOGM>
 struct Shape4 {
