@@ -106,7 +106,7 @@ int sgfhe_bootstrap_batch_device(sgfhe_ctx* ctx, int32_t batch, const uint64_t* 
                                  uint64_t* d_out_or, uint64_t* d_out_xor, void* stream);
 
 /* bootstrap(bkey, rng, ...) with the flatten draws made ON THE DEVICE by a counter-based generator (Philox4x32-10 keyed by
- * `seed`, counter = (coefficient, 2 step + polynomial, gate0 + gate index)): the randomised mode without 268 MB of host
+ * `seed`, counter = (coefficient, 2 step + polynomial, 64-bit gate0 + gate index)): the randomised mode without 268 MB of host
  * draws per gate at Params(1024).  Each draw is uniform on [-xmax, xmax] as at src/utils.jl:210-216, 229, but the stream is
  * not that of any Julia RNG -- use sgfhe_bootstrap_batch with host draws where the reference's exact stream matters.
  * seed != 0; gate0 lets sharded or successive batches use disjoint streams. */

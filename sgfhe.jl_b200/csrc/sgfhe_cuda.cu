@@ -90,11 +90,11 @@ __device__ void gate_init(const DevConst& C, const Scratch& S, uint64_t ub) {
 // Where flatten(rng, ...) (src/utils.jl:198-241) takes its draws rand(rng, -xmax:xmax) from.  ptr: the caller's values for
 // this step, [2][m][2] (polynomial a then b, coefficient, digit) -- the parity path, bit-exact with the reference for the
 // caller's RNG.  ptr == NULL and seed != 0: made on the device by the counter-based generator Philox4x32-10 (Salmon et al.,
-// SC'11), key = seed, counter = (coefficient, 2 step + polynomial, gate): no memory traffic, so the randomised mode is
+// SC'11), key = seed, counter = (coefficient, 2 step + polynomial, gate low word, gate high word ^ tag): no memory traffic, so the randomised mode is
 // usable at paper size (host draws are 268 MB per gate there).  Valid randomised ciphertexts, but a different stream
 // from any Julia RNG; the same (seed, gate, step) always gives the same draws.
 struct DrawSrc {
-  const int64_t* ptr; uint64_t seed; uint32_t gate, step;
+  const int64_t* ptr; uint64_t seed, gate; uint32_t step;
   __device__ __forceinline__ bool on() const { return ptr != nullptr || seed != 0; }
 };
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -111,7 +111,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // bits (bias below 2^-18 of one value's probability)
 __device__ __forceinline__ void get_draws(const DevConst& C, const DrawSrc& d, int c, int j, int m, int64_t& x0, int64_t& x1) {
   if (d.ptr) { x0 = d.ptr[((size_t)c * m + j) * 2]; x1 = d.ptr[((size_t)c * m + j) * 2 + 1]; return; }
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)j, 2u * d.step + (uint32_t)c, d.gate, 0x53474648u),
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)j, 2u * d.step + (uint32_t)c, (uint32_t)d.gate, 0x53474648u ^ (uint32_t)(d.gate >> 32)),
                                 make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
   x0 = (int64_t)__umul64hi((uint64_t)r.x | ((uint64_t)r.y << 32), 2 * C.xmax + 1) - (int64_t)C.xmax;
   x1 = (int64_t)__umul64hi((uint64_t)r.z | ((uint64_t)r.w << 32), 2 * C.xmax + 1) - (int64_t)C.xmax;
@@ -1096,7 +1096,7 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
     const bool pack = (A.flags & F_PACK) != 0;           // shortened_external_product batch (src/fhe.jl:632-641, 683-684)
     const int64_t* dr = A.draws ? A.draws + (size_t)g * A.draw_steps * 4 * m : nullptr;
     const uint64_t seed = A.draws ? 0 : A.rng_seed;
-    const uint32_t gid = (uint32_t)(A.rng_gate0 + (uint64_t)g);
+    const uint64_t gid = A.rng_gate0 + (uint64_t)g;
     auto draws_of = [&](int k) {                          // the draws of accumulation step k of this gate (none: deterministic)
       DrawSrc d; d.ptr = dr ? dr + (size_t)(k - (pack ? 0 : A.step_begin)) * 4 * m : nullptr; d.seed = seed; d.gate = gid; d.step = (uint32_t)k;
       return d;
@@ -1611,7 +1611,7 @@ __global__ void pack_tail_kernel(const __grid_constant__ DevConst C, const uint6
 }
 
 // test seam: the draws DrawSrc makes on the device for (seed, gate, steps step0..), as the host would have to supply them
-__global__ void device_draws_kernel(const __grid_constant__ DevConst C, uint64_t seed, uint32_t gate, int step0, int steps,
+__global__ void device_draws_kernel(const __grid_constant__ DevConst C, uint64_t seed, uint64_t gate, int step0, int steps,
                                     int64_t* __restrict__ out) {
   const int m = C.m;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2182,7 +2182,7 @@ extern "C" int sgfhe_device_draws(sgfhe_ctx* c, uint64_t seed, uint64_t gate, in
   CK(cudaSetDevice(c->device));
   const size_t count = (size_t)steps * 2 * c->hp.m;
   int rc = ensure_arena(c, count * 16); if (rc) return rc;
-  device_draws_kernel<<<(unsigned)((count + 255) / 256), 256>>>(c->dc, seed, (uint32_t)gate, step0, steps, reinterpret_cast<int64_t*>(c->d_arena));
+  device_draws_kernel<<<(unsigned)((count + 255) / 256), 256>>>(c->dc, seed, gate, step0, steps, reinterpret_cast<int64_t*>(c->d_arena));
   ++g_launches;
   CK(cudaGetLastError());
   CK(cudaMemcpy(out, c->d_arena, count * 16, cudaMemcpyDeviceToHost));

@@ -776,12 +776,12 @@ def test_device_rng_stream_is_philox(sg):
     kat = _philox4x32_10([np.zeros(1, np.uint32)] * 4, np.zeros(2, np.uint32))
     assert [int(x[0]) for x in kat] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]       # Random123 kat_vectors, philox4x32-10
     P = sg.Params(64)
-    seed, gate, step0, steps = 0x1234567890ABCDEF, 77, 3, 2
+    seed, gate, step0, steps = 0x1234567890ABCDEF, (5 << 32) + 77, 3, 2
     got = _device_draws(sg, P, seed, gate, step0, steps)
     xmax = P.B // 2 * 3
     j = np.tile(np.arange(P.m, dtype=np.uint32), steps * 2)
     sc = np.repeat(np.arange(steps * 2, dtype=np.uint32) + 2 * step0, P.m)                   # 2 step + polynomial
-    r = _philox4x32_10([j, sc, np.full_like(j, gate), np.full_like(j, 0x53474648)],
+    r = _philox4x32_10([j, sc, np.full_like(j, gate & 0xFFFFFFFF), np.full_like(j, 0x53474648 ^ (gate >> 32))],
                        np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32))
     for d, (lo, hi) in enumerate(((r[0], r[1]), (r[2], r[3]))):
         v = [((int(a) | (int(b) << 32)) * (2 * xmax + 1) >> 64) - xmax for a, b in zip(lo, hi)]
