@@ -120,64 +120,77 @@ class ClockSampler:
 # CPU arm: the oracle (a C port of the reference's algorithm; the reference itself is Julia + DarkIntegers,
 # neither present in this image) -- bench.py may execute oracle/ only here and in cpu_baseline.
 # ----------------------------------------------------------------------------------------------------------
-def _cpu_sample(so, OP, n: int, threads: int, target_s: float) -> dict:
-    """`threads` gates side by side, one per thread, literal formulation; all n steps when that fits the time budget,
-    otherwise the first `steps` of them, extrapolated linearly over the strictly sequential loop (src/fhe.jl:579-582)."""
-    so.set_setup_threads(max(threads, os.cpu_count() or 1))
-    sk = so.make_secret(OP, 1)
-    probe = min(OP.n, 4)
-    key = so.make_bkey(OP, sk, 1, rows=probe)
-    _, lwes = so.make_lwes(OP, sk, 1)
-    l1 = np.ascontiguousarray(lwes[:threads]); l2 = np.ascontiguousarray(lwes[threads:2 * threads])
-    t0 = time.perf_counter()
-    so.bootstrap_batch(OP, key, l1, l2, n_steps=probe, literal=True, threads=threads)
-    per_step = (time.perf_counter() - t0) / probe
-    steps = OP.n if per_step * OP.n <= 1.5 * target_s else int(max(probe, min(OP.n, target_s / max(per_step, 1e-9))))
-    if steps > probe:
-        key = so.make_bkey(OP, sk, 1, rows=steps)
-    t0 = time.perf_counter()
-    so.bootstrap_batch(OP, key, l1, l2, n_steps=steps, literal=True, threads=threads)
-    dt = time.perf_counter() - t0
-    gates = threads * steps / OP.n
-    how = "all %d accumulation steps (full gates)" % OP.n if steps == OP.n else \
-        "first %d of %d accumulation steps, extrapolated linearly in steps" % (steps, OP.n)
-    return {"value": gates / dt, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
-            "sample": f"{threads} gate(s) x {how} at Params({n}), literal 24-NTT/step formulation (fhe.jl:579-582), "
-                      f"{threads} thread(s); C port of SGFHE.jl's algorithm (Julia/DarkIntegers unavailable in this image)"}
+class CpuArm:
+    """The CPU arm: `threads` gates side by side, one per thread, in the oracle's literal formulation (24 transforms per
+    step, src/fhe.jl:579-582).  Key material and inputs are built once; every sample() is one timed pass."""
+
+    def __init__(self, n: int, threads: int, per_sample_s: float):
+        import sgfhe_oracle as so
+        so.build()
+        self.so, self.n, self.threads = so, n, threads
+        self.OP = OP = so.Params(n)
+        so.set_setup_threads(max(threads, os.cpu_count() or 1))
+        self.sk = so.make_secret(OP, 1)
+        probe = min(OP.n, 4)
+        key = so.make_bkey(OP, self.sk, 1, rows=probe)
+        _, lwes = so.make_lwes(OP, self.sk, 1)
+        self.l1 = np.ascontiguousarray(lwes[:threads]); self.l2 = np.ascontiguousarray(lwes[threads:2 * threads])
+        t0 = time.perf_counter()
+        so.bootstrap_batch(OP, key, self.l1, self.l2, n_steps=probe, literal=True, threads=threads)
+        per_step = (time.perf_counter() - t0) / probe
+        # all n steps (full gates) when that fits the budget, otherwise a prefix of the strictly sequential loop
+        self.steps = OP.n if per_step * OP.n <= 1.5 * per_sample_s else int(max(probe, min(OP.n, per_sample_s / max(per_step, 1e-9))))
+        self.key = key if self.steps <= probe else so.make_bkey(OP, self.sk, 1, rows=self.steps)
+
+    def sample(self) -> dict:
+        OP = self.OP
+        t0 = time.perf_counter()
+        self.so.bootstrap_batch(OP, self.key, self.l1, self.l2, n_steps=self.steps, literal=True, threads=self.threads)
+        dt = time.perf_counter() - t0
+        gates = self.threads * self.steps / OP.n                   # linear in the number of sequential steps
+        how = "all %d accumulation steps (full gates)" % OP.n if self.steps == OP.n else \
+            "first %d of %d accumulation steps, extrapolated linearly in steps" % (self.steps, OP.n)
+        return {"value": gates / dt, "unit": UNIT, "cores": self.threads, "kind": "port", "seconds": dt,
+                "sample": f"{self.threads} gate(s) x {how} at Params({self.n}), literal 24-NTT/step formulation (fhe.jl:579-582), "
+                          f"{self.threads} thread(s); C port of SGFHE.jl's algorithm (Julia/DarkIntegers unavailable in this image)"}
 
 
 def cpu_gates_per_s(n: int, target_s: float, threads: int | None = None, with_single: bool = True) -> dict:
-    """The CPU arm.  `value` is the all-threads figure (independent gates side by side: the most the host can do);
-    `single_thread` is the figure closest to the reference itself, which is single-threaded (no Threads / Distributed
-    anywhere in src/)."""
-    import sgfhe_oracle as so
-    so.build()
-    OP = so.Params(n)
+    """`value` is the all-threads figure (independent gates side by side: the most the host can do); `single_thread` is the
+    figure closest to the reference itself, which is single-threaded (no Threads / Distributed anywhere in src/)."""
     threads = threads or os.cpu_count() or 1
-    out = _cpu_sample(so, OP, n, threads, target_s)
+    out = CpuArm(n, threads, target_s).sample()
     out["host_cores"] = os.cpu_count()
     if with_single and threads > 1:
-        one = _cpu_sample(so, OP, n, 1, max(target_s / 3, 3.0))
+        one = CpuArm(n, 1, max(target_s / 3, 3.0)).sample()
         out["single_thread"] = {k: one[k] for k in ("value", "unit", "cores", "seconds", "sample")}
     return out
 
 
 def run_reference(args) -> None:
+    """--impl reference: K timed passes of the CPU arm.  A full gate is 1024 strictly sequential steps (about 27 s per gate
+    and thread at Params(1024)), so with many steps requested each pass is a prefix of the loop sized to keep the whole run
+    near three minutes; with few steps it is whole gates."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_s = 20.0
+    threads = args.cpu_threads or os.cpu_count() or 1
+    per_step_s = min(30.0, max(3.0, 180.0 / max(args.steps, 1)))
+    arm = CpuArm(args.n, threads, per_step_s)
+    warm = CpuArm(args.n, threads, 1.0) if args.warmup else None
     for _ in range(args.warmup):
-        cpu_gates_per_s(args.n, 2.0, args.cpu_threads, with_single=False)
-    vals = []
+        warm.sample()
+    vals, last = [], None
     t0 = time.perf_counter()
-    last = None
-    for k in range(args.steps):
-        last = cpu_gates_per_s(args.n, per_step_s, args.cpu_threads, with_single=(k == args.steps - 1))
+    for _ in range(args.steps):
+        last = arm.sample()
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    cb = dict(last); cb["value"] = v
+    cb = dict(last); cb["value"] = v; cb["host_cores"] = os.cpu_count()
+    if threads > 1:
+        one = CpuArm(args.n, 1, 5.0).sample()
+        cb["single_thread"] = {k: one[k] for k in ("value", "unit", "cores", "seconds", "sample")}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
@@ -492,7 +505,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="budget of the cpu_baseline sample: 30 s fits whole gates at Params(1024)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores); a one-thread figure is reported next to it")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --batch is the TOTAL over all GPUs")
     ap.add_argument("--wiring", default="local", choices=["local", "allgather"], help="depth workload: layer inputs from this rank only, or all-gathered and permuted across ranks")
