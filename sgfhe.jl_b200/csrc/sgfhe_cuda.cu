@@ -1155,7 +1155,7 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
 }
 
 template <int LOGM>
-__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1024 / Shape<LOGM>::T)
 bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int m = 1 << LOGM;
@@ -1210,7 +1210,7 @@ static constexpr size_t kSmemV5 = (size_t)6 * Shape5::HALF * 4 + (size_t)2 * Sha
 // Key pre-transform (K10): coefficient-form wide polys -> per-prime NTT domain, Montgomery form.
 // grid = (npolys, L).  coef: [npolys][m][2];  out: poly P of row k=P/8, slot jc=P%8 -> keyhat[((k L + i) 8 + jc) m ..]
 template <int LOGM>
-__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1024 / Shape<LOGM>::T)
 key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ coef, uint32_t* __restrict__ keyhat,
                      const uint2* __restrict__ tw_f, int poly0) {
   extern __shared__ __align__(16) uint32_t sm[];
@@ -1252,7 +1252,7 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
 // Standalone negacyclic product of two full-size operands (seam for DarkIntegers `Polynomial *`).
 // grid = batch CTAs; scratch per CTA: [LM][m] u32.
 template <int LOGM>
-__global__ void __launch_bounds__(Shape<LOGM>::T, 1)
+__global__ void __launch_bounds__(Shape<LOGM>::T, 1024 / Shape<LOGM>::T)
 polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ a, const uint64_t* __restrict__ b,
                uint64_t* __restrict__ out, const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
                uint32_t* scratch, int batch, int b_bcast) {
@@ -2404,7 +2404,7 @@ extern "C" int sgfhe_bkey_generate(sgfhe_ctx* c, const uint8_t* sk, const uint64
     CK(cudaMemcpyAsync(d + o_e, e_rand + (size_t)done * 4 * m, polys * m * 8, cudaMemcpyHostToDevice, nullptr));
     {                                                   // products a_j * ext_key, second operand broadcast
       const bool v4 = c->use_v4 && !getenv("SGFHE_POLYMUL_V3");
-      const int cap = v4 ? c->num_sms : c->num_sms * 2, units = v4 ? ((int)polys + 1) / 2 : (int)polys;
+      const int cap = v4 ? c->num_sms : c->num_sms * std::max(2, 1024 / c->threads), units = v4 ? ((int)polys + 1) / 2 : (int)polys;
       const int grid = units < cap ? units : cap;
       if (grid > c->pm_ctas) {
         cudaFree(c->d_pm_scratch); c->d_pm_scratch = nullptr; c->pm_ctas = 0;
@@ -2603,7 +2603,8 @@ extern "C" int sgfhe_polymul_device(sgfhe_ctx* c, int32_t batch, const uint64_t*
   if (batch == 0) return SGFHE_OK;
   CK(cudaSetDevice(c->device));
   const bool v4 = c->use_v4 && !getenv("SGFHE_POLYMUL_V3");
-  const int cap = v4 ? c->num_sms : c->num_sms * 2, units = v4 ? (batch + 1) / 2 : batch;     // v4: one CTA per SM, two products at a time
+  // v4: one CTA per SM, two products at a time; small-m kernel: 64 registers per thread, as many CTAs as 1024 threads allow (at least two)
+  const int cap = v4 ? c->num_sms : c->num_sms * std::max(2, 1024 / c->threads), units = v4 ? (batch + 1) / 2 : batch;
   const int grid = units < cap ? units : cap;
   if (grid > c->pm_ctas) {
     cudaFree(c->d_pm_scratch); c->d_pm_scratch = nullptr; c->pm_ctas = 0;
