@@ -38,9 +38,13 @@ struct DevConst {
   uint32_t r32_sh[MAXP], r64_sh[MAXP];      // their Shoup companions
   uint64_t Qhalf[2];                        // floor(Q / 2) as (lo, hi)
   uint32_t mont[MAXP], mont_sh[MAXP];       // 2^32 mod p as a Shoup constant
+  // Pre-transformed key words carry 2^32 (Montgomery form) AND scale[0] = -m^-1 (P_L/p)^-1: the external product is linear in
+  // the key, so the CRT pre-scaling costs nothing per step (it used to be one extra multiplication per coefficient pair in
+  // the last inverse stage).  lastw = psi^(-m/2), the bare twiddle of that stage.
+  uint32_t keymul[MAXP], keymul_sh[MAXP];
+  uint32_t lastw[MAXP], lastw_sh[MAXP];
   uint32_t dig_negc[MAXP];                  // p - (2^46 mod p) - 4p (mod 2^32), see digit_mod
   uint32_t scale[2][MAXP], scale_sh[2][MAXP];   // [0]: -m^-1 (P_L/p)^-1 (digits are transformed negated) ; [1]: 2^32 m^-1 (P_LM/p)^-1  (mod p)
-  uint32_t scale_w[MAXP], scale_w_sh[MAXP];     // scale[0] * psi^(-m/2): the last inverse stage with the CRT pre-scaling folded in
   uint32_t scale_w1[MAXP], scale_w1_sh[MAXP];   // the same for scale[1] (standalone products)
   uint2 topf[MAXP][15], topi[MAXP][15];     // v4 kernels: twiddles of the top stages held in registers (forward, inverse), index k - 1 for tw[k]
   uint2 topf_h[MAXP][2][7], topi_h[MAXP][2][7];   // v5: per half h of a radix-16 group, the radix-8 after / before its first stage (direct / inverse table entries)

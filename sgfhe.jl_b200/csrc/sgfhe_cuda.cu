@@ -375,7 +375,6 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     ntt_passes<LOGM, 2, false>(sm, tab, p, C.zero);
     SGFHE_TICK(3);
     {
-      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i];
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_i + (size_t)i * m, wt);
 #pragma unroll 4
@@ -387,7 +386,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
         inv_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k)
-          S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(shoup_mul(x[k], sc, scs, p), p);
+          S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(x[k], p);   // the CRT pre-scaling rides in the key words
       }
     }
     __syncthreads();
@@ -654,7 +653,8 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
           const uint32_t kb[8] = {kk[2].x, kk[2].y, kk[2].z, kk[2].w, kk[3].x, kk[3].y, kk[3].z, kk[3].w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const uint32_t d = min(x[e], x[e] - p2);                 // [0, 2p): four products < 8 p^2 < 2^63
+            // only two of the four transforms are corrected to [0, 2p): T < 2 (2p + 4p) p = 12 p^2, T + q p < 12 p^2 + 2^32 p < 2^64
+            const uint32_t d = j < 2 ? min(x[e], x[e] - p2) : x[e];
             sa[e] += (uint64_t)d * ka[e];
             sb[e] += (uint64_t)d * kb[e];
           }
@@ -663,7 +663,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
         block_twiddles<false>(tab, m / 8, blk, p, wi);
         uint32_t ya[8], yb[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {                                // redc of T < 8 p^2 lands in [0, 3p)
+        for (int e = 0; e < 8; ++e) {                                // redc of T < 12 p^2 lands in [0, 4p)
           ya[e] = redc(sa[e], p, pinv); ya[e] = min(ya[e], ya[e] - p2);
           yb[e] = redc(sb[e], p, pinv); yb[e] = min(yb[e], yb[e] - p2);
         }
@@ -695,9 +695,9 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(3);
     // ---- top inverse stages in registers + CRT pre-scaling + store of the residues --------------------------
-    // last level: x' = (x + y) s, y' = (x - y) psi^(-m/2) s with s = m^-1 (P/p)^-1 folded into both multiplications
+    // last level: x' = x + y, y' = (x - y) psi^(-m/2); the scaling s = m^-1 (P/p)^-1 rides in the key words (DevConst::keymul)
     {
-      const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i], sw = C.scale_w[i], sws = C.scale_w_sh[i];
+      const uint32_t sw = C.lastw[i], sws = C.lastw_sh[i];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t x[R0];
@@ -707,7 +707,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll
         for (int k = 0; k < R0 / 2; ++k) {
           const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
-          S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(shoup_mul(s0, sc, scs, p), p);
+          S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(min(s0, s0 - p2), p);
           S.zres[((size_t)i * 2 + c) * m + tid + (k + R0 / 2) * T] = csub(shoup_mul(d0, sw, sws, p), p);
         }
       }
@@ -1038,7 +1038,7 @@ __device__ void gate_step_v5(const DevConst& C, const Scratch& S, uint32_t* sm, 
       SGFHE_TICK(3);
       // ---- inverse top stages of this half in registers; the last stage joins the two halves ----
       {
-        const uint32_t sc = C.scale[0][i], scs = C.scale_sh[0][i], sw = C.scale_w[i], sws = C.scale_w_sh[i];
+        const uint32_t sw = C.lastw[i], sws = C.lastw_sh[i];
 #pragma unroll
         for (int item = 0; item < 4; ++item) {             // item = 2 c + group
           const int c = item >> 1, t = tid + (item & 1) * T;
@@ -1055,7 +1055,7 @@ __device__ void gate_step_v5(const DevConst& C, const Scratch& S, uint32_t* sm, 
             for (int k = 0; k < 8; ++k) {
               const uint32_t y0 = pk[k * T];               // first half's value of the pair (k, k + 8)
               const uint32_t s0 = y0 + x[k] + z, d0 = y0 - x[k] + p2;
-              S.zres[((size_t)i * 2 + c) * m + t + k * 512] = csub(shoup_mul(s0, sc, scs, p), p);
+              S.zres[((size_t)i * 2 + c) * m + t + k * 512] = csub(min(s0, s0 - p2), p);
               S.zres[((size_t)i * 2 + c) * m + t + (k + 8) * 512] = csub(shoup_mul(d0, sw, sws, p), p);
             }
           }
@@ -1245,7 +1245,7 @@ key_transform_kernel(const __grid_constant__ DevConst C, const uint64_t* __restr
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     uint32_t v = sm[swz(idx)];
     v = min(v, v - p2); v = min(v, v - p);
-    dst[key_pos<LOGM>(idx)] = csub(shoup_mul(v, C.mont[i], C.mont_sh[i], p), p);
+    dst[key_pos<LOGM>(idx)] = csub(shoup_mul(v, C.keymul[i], C.keymul_sh[i], p), p);   // 2^32 (Montgomery) and the CRT pre-scaling
   }
 }
 
@@ -1744,8 +1744,9 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
       dc->scale_sh[basis][i] = (uint32_t)((sc << 32) / p);
       if (basis == 0) {                                   // psi^(-m/2) = (psi^-1)^(m/2)
         const uint64_t psi_inv = h_powmod64(h_root_2m(p, hp.m), p - 2, p);
-        const uint64_t sw = h_mulmod64(sc, h_powmod64(psi_inv, hp.m / 2, p), p);
-        dc->scale_w[i] = (uint32_t)sw; dc->scale_w_sh[i] = (uint32_t)((sw << 32) / p);
+        const uint64_t lw = h_powmod64(psi_inv, hp.m / 2, p), km = h_mulmod64(sc, dc->r32[i], p);
+        dc->lastw[i] = (uint32_t)lw; dc->lastw_sh[i] = (uint32_t)((lw << 32) / p);
+        dc->keymul[i] = (uint32_t)km; dc->keymul_sh[i] = (uint32_t)((km << 32) / p);
       } else {
         const uint64_t psi_inv = h_powmod64(h_root_2m(p, hp.m), p - 2, p);
         const uint64_t sw = h_mulmod64(sc, h_powmod64(psi_inv, hp.m / 2, p), p);
@@ -2067,7 +2068,7 @@ extern "C" int sgfhe_bkey_export(sgfhe_ctx* c, int32_t rows, void* blob, uint64_
   if (!blob || bytes < need) return fail(SGFHE_ERR_ARG, "blob buffer too small");
   CK(cudaSetDevice(c->device));
   KeyBlobHeader h; memset(&h, 0, sizeof h);
-  h.magic = KEY_MAGIC; h.version = 2; h.n = c->hp.n; h.m = c->hp.m; h.L = c->dc.L; h.rows = rows;
+  h.magic = KEY_MAGIC; h.version = 3; h.n = c->hp.n; h.m = c->hp.m; h.L = c->dc.L; h.rows = rows;
   for (int i = 0; i < MAXP; ++i) h.p[i] = c->dc.p[i];
   h.Q[0] = (uint64_t)c->hp.Q; h.Q[1] = (uint64_t)(c->hp.Q >> 64);
   memcpy(blob, &h, sizeof h);
@@ -2078,7 +2079,7 @@ extern "C" int sgfhe_bkey_export(sgfhe_ctx* c, int32_t rows, void* blob, uint64_
 extern "C" int sgfhe_bkey_import(sgfhe_ctx* c, const void* blob, uint64_t bytes) {
   if (!c || !blob || bytes < sizeof(KeyBlobHeader)) return fail(SGFHE_ERR_ARG, "bad blob");
   KeyBlobHeader h; memcpy(&h, blob, sizeof h);
-  if (h.magic != KEY_MAGIC || h.version != 2) return fail(SGFHE_ERR_ARG, "not a serialised sgfhe key");
+  if (h.magic != KEY_MAGIC || h.version != 3) return fail(SGFHE_ERR_ARG, "not a serialised sgfhe key");
   if (h.n != c->hp.n || h.m != c->hp.m || h.L != c->dc.L || h.Q[0] != (uint64_t)c->hp.Q || h.Q[1] != (uint64_t)(c->hp.Q >> 64))
     return fail(SGFHE_ERR_ARG, "serialised key belongs to other parameters");
   for (int i = 0; i < h.L; ++i) if (h.p[i] != c->dc.p[i]) return fail(SGFHE_ERR_ARG, "serialised key uses another RNS basis");
