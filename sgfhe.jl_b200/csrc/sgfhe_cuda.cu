@@ -283,6 +283,119 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
 #undef SGFHE_TICK
 }
 
+// Tail of the v4 step with the two halves of the CTA on different work (T = 512 threads, 16 warps, four per scheduler).
+// crt_update runs CRT(0), update(0), CRT(1), update(1) one after the other with all warps in the same phase: the CRT sums
+// keep the FMA-heavy pipe busy (18 IMAD.WIDE per coefficient) while the ALU and FP64 pipes idle, the update / decomposition
+// does the opposite.  Here warps 0-7 update polynomial 0 while warps 8-15 form the CRT sums of polynomial 1, so every
+// scheduler holds two warps of each kind and interleaves them cycle by cycle:
+//   A  all warps:  CRT sums of polynomial 0 -> shared memory (all 128 KiB of the transform buffers)
+//   B  warps 0-7:  update + decomposition of polynomial 0 from shared memory
+//      warps 8-15: CRT sums of polynomial 1 -> global scratch S.sums (shared memory is still occupied)
+//   C  all warps:  update + decomposition of polynomial 1, sums read back from L2 (ld.cg)
+// MEASURED (round 2, gpurun_out/r2_ab12.txt): bit-exact, B takes 16.8k cycles against 21.0k for the two phases it replaces,
+// but C takes 27.3k against 10.4k -- 256 KiB of sums per step come back through the 42 B/clk/SM L2 port, and shared memory
+// cannot hold both polynomials' sums (2 x 128 KiB).  214.1k cycles/step against 198.4k: compiled only with -DSGFHE_TAIL_SPLIT.
+#ifdef SGFHE_TAIL_SPLIT
+template <int LOGM, int T, bool F64>
+__device__ __forceinline__ void crt_update_split(const DevConst& C, const Scratch& S, uint4* sm4, uint32_t* stg,
+                                                 const DrawSrc draws_next, int u, bool ext, bool decompose_next,
+                                                 unsigned long long* timing, long long& tprev) {
+  constexpr int m = 1 << LOGM, L = Shape<LOGM>::L, TH = T / 2, D = 4;
+  static_assert((m / T) % D == 0, "tail pipelines are D deep");
+  const int tid = threadIdx.x;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+#define SGFHE_UPDATE(TT, CC, GS, SRC) do { \
+    if (ext) { \
+      if (!decompose_next) update_poly<LOGM, TT, D, true, false, false, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+      else if (draws_next.on()) update_poly<LOGM, TT, D, true, true, true, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+      else update_poly<LOGM, TT, D, true, true, false, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+    } else { \
+      if (!decompose_next) update_poly<LOGM, TT, D, false, false, false, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+      else if (draws_next.on()) update_poly<LOGM, TT, D, false, true, true, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+      else update_poly<LOGM, TT, D, false, true, false, F64, GS>(C, S, SRC, CC, draws_next, u, aq); \
+    } } while (0)
+  // ---- A: CRT sums of polynomial 0 (each thread reads only residues it stored itself: loads precede the barrier) ----
+  {
+    uint32_t yq[D][L];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int i = 0; i < L; ++i) yq[d][i] = S.zres[(size_t)i * 2 * m + tid + d * T];
+    __syncthreads();                                         // shared memory free for the CRT staging
+    // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT sums run
+    for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
+#pragma unroll 1
+    for (int it0 = 0; it0 < m / T; it0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int idx = tid + (it0 + d) * T;
+        sm4[idx] = crt_sum<0, L>(C, yq[d], 1);
+        if (it0 + d + D < m / T) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) yq[d][i] = S.zres[(size_t)i * 2 * m + idx + D * T];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  SGFHE_TICK(5);
+  // ---- B: update(0) on warps 0-7, CRT(1) on warps 8-15 ----
+  if (tid < TH) {
+    u96 aq[D];
+    if (!ext) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) aq[d] = ld96(S.acc, m, tid + d * TH);
+    }
+    SGFHE_UPDATE(TH, 0, false, sm4);
+  } else {
+    const int t2 = tid - TH;
+    const uint32_t* zr = S.zres + (size_t)m;
+    uint32_t yq[D][L];
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int i = 0; i < L; ++i) yq[d][i] = __ldcg(&zr[(size_t)i * 2 * m + t2 + d * TH]);
+#pragma unroll 1
+    for (int it0 = 0; it0 < m / TH; it0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int idx = t2 + (it0 + d) * TH;
+        __stcg(&S.sums[idx], crt_sum<0, L>(C, yq[d], 1));
+        if (it0 + d + D < m / TH) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) yq[d][i] = __ldcg(&zr[(size_t)i * 2 * m + idx + D * TH]);
+        }
+      }
+    }
+  }
+  // accumulator words of the first D iterations of phase C: async copies into the idle twiddle-table region
+  if (!ext) {
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int l = 0; l < 3; ++l) cp_async4(stg + (d * 3 + l) * T + tid, S.acc + (3 + l) * m + tid + d * T);
+    cp_async_commit();
+  }
+  __syncthreads();
+  SGFHE_TICK(6);
+  // ---- C: update(1), sums from L2 ----
+  {
+    u96 aq[D];
+    if (!ext) {
+      cp_async_wait_all();
+#pragma unroll
+      for (int d = 0; d < D; ++d) { aq[d].x0 = stg[(d * 3) * T + tid]; aq[d].x1 = stg[(d * 3 + 1) * T + tid]; aq[d].x2 = stg[(d * 3 + 2) * T + tid]; }
+    }
+    SGFHE_UPDATE(T, 1, true, S.sums);
+  }
+  __syncthreads();
+  SGFHE_TICK(7);
+#undef SGFHE_UPDATE
+#undef SGFHE_TICK
+}
+#endif
+
 // One accumulation step (body of src/fhe.jl:579-582) on digits already in S.dig; leaves the new accumulator in
 // S.acc and its decomposition (with `draws_next`, the following step's draws) in S.dig.  u = rotation in [0, 2m).
 template <int LOGM>
@@ -714,7 +827,11 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     SGFHE_TICK(4);
   }
+#ifdef SGFHE_TAIL_SPLIT                                   // measured slower: kept for A/B builds only
+  crt_update_split<LOGM, T, HF>(C, S, reinterpret_cast<uint4*>(sm), sm + 4 * m, draws_next, u, ext, decompose_next, timing, tprev);
+#else
   crt_update<LOGM, T, true, HF>(C, S, reinterpret_cast<uint4*>(sm), sm + 4 * m, draws_next, u, ext, decompose_next, timing, tprev);   // begins with the barrier that frees shared memory
+#endif
   if (tid == 0) stage_table(tab, tw_f, m * 8, bar);      // ends with a barrier: the staging area is free again
 #undef SGFHE_TICK
 }
@@ -2128,9 +2245,9 @@ extern "C" int sgfhe_bootstrap_batch_device(sgfhe_ctx* c, int32_t batch, const u
     A.timing = d_t;
     int rc = launch_gates(c, A, (cudaStream_t)stream);
     CK(cudaDeviceSynchronize()); CK(cudaMemcpy(h_t, d_t, sizeof h_t, cudaMemcpyDeviceToHost)); cudaFree(d_t);
-    static const char* names[7] = {"digit load+top stage", "forward passes", "pointwise", "inverse passes", "top stage+store", "crt", "update+decompose"};
-    unsigned long long tot = 0; for (int i = 0; i < 7; ++i) tot += h_t[i];
-    for (int i = 0; i < 7; ++i) fprintf(stderr, "[sgfhe phase] %-22s %12llu cycles  %5.1f%%\n", names[i], h_t[i], 100.0 * h_t[i] / (tot ? tot : 1));
+    static const char* names[8] = {"digit load+top stage", "forward passes", "pointwise", "inverse passes", "top stage+store", "crt", "update+decompose", "tail C (split tail)"};
+    unsigned long long tot = 0; for (int i = 0; i < 8; ++i) tot += h_t[i];
+    for (int i = 0; i < 8; ++i) if (i < 7 || h_t[i]) fprintf(stderr, "[sgfhe phase] %-22s %12llu cycles  %5.1f%%\n", names[i], h_t[i], 100.0 * h_t[i] / (tot ? tot : 1));
     fprintf(stderr, "[sgfhe phase] total %llu cycles over %d steps = %.0f cycles/step\n", tot, c->hp.n, (double)tot / c->hp.n);
     return rc;
   }
