@@ -26,7 +26,8 @@ struct DevConst {
   uint32_t zero;                // always 0; a constant-bank operand ptxas cannot fold (forces 3-input IADD3 on the ALU pipe)
   u128 Q, DQ, offs, B;          // offs = s * (1 + B) mod Q (src/utils.jl:169)
   uint64_t s;                   // digit offset (src/utils.jl:162-166)
-  uint64_t s46;                 // 2^46 - s: bias of the stored digit words minus the digit offset
+  uint64_t s46;                 // dig_bias - s: bias of the stored digit words minus the digit offset
+  uint64_t dig_bias;            // 2^46 (n <= 1024: |digit| <= 2B < 2^45) or 2^48 (n = 2048: 2B < 2^47.2)
   uint64_t xmax;                // 3 (B / 2): draws of the randomised flatten are uniform on [-xmax, xmax] (src/utils.jl:210-216)
   double barrett_inv;           // 2^(sbits-16) / Q, scaled by (1 - 2^-40): never above the true value
   double inv35;                 // 1/35 rounded up
@@ -228,11 +229,15 @@ struct Shape {
   static constexpr int NPASS = LOGM / 3;
   static constexpr int G = M / 8;
   static constexpr int T = (M / 2 > 1024) ? 1024 : M / 2;
-  static constexpr int NG = T / G;
+  static constexpr int NG = T / G > 0 ? T / G : 1;
+  static constexpr int LPT = G > T ? G / T : 1;   // radix-8 blocks per thread and polynomial when one polynomial has more blocks than the CTA threads (m = 16384)
   static constexpr int STR = M >> REM;       // stride of the fused top stages
   // RNS basis sizes implied by Params(n), m = 8n (checked against the host derivation in sgfhe_ctx_create)
-  static constexpr int L = LOGM <= 10 ? 4 : 5;                        // bootstrap external product
+  static constexpr int L = LOGM <= 10 ? 4 : (LOGM <= 13 ? 5 : 6);     // bootstrap external product
   static constexpr int LM = LOGM <= 10 ? 5 : (LOGM <= 12 ? 6 : 7);    // product of two full-size operands
+  // m = 16384 (Params(2048), 93-bit Q): four transform buffers (256 KiB) do not fit an SM, so the "wide" kernels work on two
+  // polynomials at a time and read their twiddles from global memory (L1/L2) instead of a staged table
+  static constexpr bool WIDE = LOGM >= 14;
 };
 
 // One radix-8 pass (active bits [B, B+3)) over NPOLY polynomials in shared memory.
@@ -242,9 +247,12 @@ template <int LOGM, int NPOLY, bool FWD, int B>
 __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
   using S = Shape<LOGM>;
   constexpr int M = S::M;
-  const int grp = threadIdx.x / S::G, lane = threadIdx.x % S::G;
+  const int grp = S::LPT > 1 ? 0 : threadIdx.x / S::G;
   if (grp >= NPOLY) return;
   const uint32_t p2 = 2 * p;
+#pragma unroll 1
+  for (int lq = 0; lq < S::LPT; ++lq) {
+  const int lane = S::LPT > 1 ? (int)threadIdx.x + lq * S::T : (int)threadIdx.x % S::G;
   const int base = ((lane >> B) << (B + 3)) | (lane & ((1 << B) - 1));
   const int t1 = (M >> (B + 3)) + (lane >> B);
   uint2 w[7];
@@ -284,6 +292,7 @@ __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* tw, uint32_
         for (int j = 0; j < 8; ++j) s[off[j]] = x[j];
       }
     }
+  }
   }
 }
 
@@ -358,7 +367,7 @@ __device__ __forceinline__ u128 negmodQ(u128 a, u128 Q) { return a ? Q - a : (u1
 
 // The accumulator is kept in OFFSET FORM a + offs mod Q (offs = s (1 + B), src/utils.jl:169,179), so the
 // decomposition starts at the divrem.  flatten(nothing, a, Val(B), Val(2)) (src/utils.jl:155-189) on a_off = a + offs:
-// returns the biased digit words dp_i = u_i - s + 2^46.  KB = log2(B / 35) = 3 LOGM - 1 (B = 35 r^2 n, src/fhe.jl:87).
+// returns the biased digit words dp_i = u_i - s + dig_bias (2^46; 2^48 at n = 2048).  KB = log2(B / 35) = 3 LOGM - 1 (B = 35 r^2 n, src/fhe.jl:87).
 template <int KB>
 __device__ __forceinline__ void decompose_off(const DevConst& C, u96 a, uint64_t& dp0, uint64_t& dp1) {
   // divrem(a, B), B = 35 2^KB   (src/utils.jl:172);  t = a >> KB < 35^2 2^KB < 2^49
@@ -374,7 +383,7 @@ __device__ __forceinline__ void decompose_off(const DevConst& C, u96 a, uint64_t
   const uint32_t rem = (uint32_t)t - 35u * q_lo;                    // < 35
   const uint64_t u1 = (uint64_t)q_lo | ((uint64_t)q_hi << 32);
   const uint64_t u0 = ((uint64_t)rem << KB) | lo;
-  dp0 = u0 + C.s46;                               // - s  (src/utils.jl:183-185), + 2^46 storage bias
+  dp0 = u0 + C.s46;                               // - s  (src/utils.jl:183-185), + storage bias
   dp1 = u1 + C.s46;
 }
 
@@ -394,13 +403,13 @@ __device__ __forceinline__ u96 off96(const DevConst& C) { u96 o; o.x0 = C.offl[0
 __device__ __forceinline__ u96 to_offset_form(const DevConst& C, u96 a) { return addmod96(a, off96(C), Q96(C)); }
 __device__ __forceinline__ u96 from_offset_form(const DevConst& C, u96 a) { return submod96(a, off96(C), Q96(C)); }
 
-// Signed digits (|d| < 2^46) are stored biased, dp = d + 2^46, as two words: lo = dp mod 2^32, hi = dp >> 18.
+// Signed digits (|d| < dig_bias) are stored biased, dp = d + dig_bias < 2^49, as two words: lo = dp mod 2^32, hi = dp >> 18.
 __device__ __forceinline__ void digit_words(uint64_t dp, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18); }
 // the NEGATED digit as a double (exact): bits 0x433 | dp are 2^52 + dp, and (2^52 + 2^46) - (2^52 + dp) = -d
 __device__ __forceinline__ double digit_f64(uint64_t dp) {
   return __dadd_rn(4573968371548160.0, -__hiloint2double((int)(0x43300000u | (uint32_t)(dp >> 32)), (int)(uint32_t)dp));
 }
-// residue of the NEGATED digit mod p in (p, 4p]: mu = floor(2^50 / p), negc4 = p - (2^46 mod p) - 4p (mod 2^32).
+// residue of the NEGATED digit mod p in (p, 4p]: mu = floor(2^50 / p), negc4 = p - (dig_bias mod p) - 4p (mod 2^32).
 // q p - (lo + negc4) is one IMAD with a negated addend; lo - q p + negc would need an extra register move to negate q.
 // All four digit polynomials change sign together, which the CRT pre-scaling constants of the bootstrap basis undo
 // (scale[0], scale_w are stored negated).

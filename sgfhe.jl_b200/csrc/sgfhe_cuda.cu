@@ -509,6 +509,77 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
 #undef SGFHE_TICK
 }
 
+// One accumulation step at m = 16384 (Params(2048): 93-bit Q, six primes).  Four transform buffers would be 256 KiB, so a
+// prime is processed in two halves of two digit polynomials each (128 KiB of shared memory): half 0 transforms digits 0, 1
+// and parks its share of the two key MAC sums (Montgomery-reduced words, thread-private) in global scratch, half 1 adds the
+// share of digits 2, 3 and both result polynomials are transformed back.  Twiddles come from global memory (a table is
+// 128 KiB per prime and direction); the unreduced CRT sums of the tail are staged in global scratch as well.
+// Correctness-first: every stage is the generic building block of gate_step.
+template <int LOGM>
+__device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
+                               const uint2* __restrict__ tw_f, const uint2* __restrict__ tw_i,
+                               const DrawSrc draws_next, int u, bool ext, bool decompose_next, unsigned long long* timing) {
+  using SH = Shape<LOGM>;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T, L = SH::L;
+  const int tid = threadIdx.x;
+  long long tprev = timing ? clock64() : 0;
+#pragma unroll 1
+  for (int i = 0; i < L; ++i) {
+    const uint32_t p = C.p[i], p2 = 2 * p, pinv = C.pinv_neg[i];
+    const uint2* twf = tw_f + (size_t)i * m;
+    const uint2* twi = tw_i + (size_t)i * m;
+    const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
+    const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
+    uint2 wt[R > 1 ? R - 1 : 1];
+    top_twiddles<REM>(twf, wt);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      for (int e = tid; e < 2 * STR; e += T) {
+        const int jj = e / STR, idx = e % STR, j = 2 * h + jj;
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.diglo[j * m + idx + k * STR], S.dighi[j * m + idx + k * STR], mu, negc, p);
+        fwd_block<REM>(x, wt, p, p2, C.zero);
+#pragma unroll
+        for (int k = 0; k < R; ++k) sm[jj * m + swz(idx + k * STR)] = x[k];
+      }
+      __syncthreads();
+      ntt_passes<LOGM, 2, true>(sm, twf, p, C.zero);
+      const uint32_t* Kh = K + (size_t)(4 * h) * m;      // key rows 2 j + c of digit polynomials j = 2h, 2h + 1
+      for (int idx = tid; idx < m; idx += T) {
+        const int si = swz(idx), kp = key_pos<LOGM>(idx);
+        uint32_t d0 = sm[si], d1 = sm[m + si];
+        d0 = min(d0, d0 - p2); d0 = min(d0, d0 - p); d1 = min(d1, d1 - p2); d1 = min(d1, d1 - p);
+        const uint64_t sa = (uint64_t)d0 * __ldg(&Kh[kp]) + (uint64_t)d1 * __ldg(&Kh[2 * m + kp]);
+        const uint64_t sb = (uint64_t)d0 * __ldg(&Kh[m + kp]) + (uint64_t)d1 * __ldg(&Kh[3 * m + kp]);
+        uint32_t ra = redc(sa, p, pinv), rb = redc(sb, p, pinv);              // [0, 2p)
+        if (h == 0) { S.park[idx] = ra; S.park[m + idx] = rb; }              // read back by this same thread
+        else {
+          ra += S.park[idx]; rb += S.park[m + idx];
+          sm[si] = min(ra, ra - p2); sm[m + si] = min(rb, rb - p2);          // [0, 2p): input range of the inverse butterflies
+        }
+      }
+      __syncthreads();
+    }
+    ntt_passes<LOGM, 2, false>(sm, twi, p, C.zero);
+    {
+      uint2 wti[R > 1 ? R - 1 : 1];
+      top_twiddles<REM>(twi, wti);
+      for (int e = tid; e < 2 * STR; e += T) {
+        const int c = e / STR, idx = e % STR;
+        uint32_t x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = sm[c * m + swz(idx + k * STR)];
+        inv_block<REM>(x, wti, p, p2, C.zero);
+#pragma unroll
+        for (int k = 0; k < R; ++k) S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(x[k], p);   // the CRT pre-scaling rides in the key words
+      }
+    }
+    __syncthreads();
+  }
+  crt_update<LOGM, T, false, false, true>(C, S, S.sums, nullptr, draws_next, u, ext, decompose_next, timing, tprev);
+}
+
 // extract + AND/OR/XOR assembly (src/fhe.jl:585-592) + reduce_modulus (src/fhe.jl:616-618)
 __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_and, uint64_t* out_or,
                            uint64_t* out_xor, bool raw) {
@@ -1252,6 +1323,7 @@ __device__ __forceinline__ void run_gates(const DevConst& C, const GateArgs& A, 
       unsigned long long* tm = blockIdx.x == 0 ? A.timing : nullptr;
       if constexpr (VER == 5) gate_step_v5(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, tab + Shape5::TABN, bar, parity, tm);
       else if constexpr (VER == 4) gate_step_v4<LOGM, HF>(C, S, sm, keyrow, A.tw_f, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
+      else if constexpr (Shape<LOGM>::WIDE) gate_step_wide<LOGM>(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tm);
       else gate_step<LOGM>(C, S, sm, keyrow, A.tw_f, A.tw_i, dn, u, (A.flags & F_EXT) != 0, more, tab, bar, parity, tm);
     }
     if (A.trace) {
@@ -1276,12 +1348,13 @@ __global__ void __launch_bounds__(Shape<LOGM>::T, 1024 / Shape<LOGM>::T)
 bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int m = 1 << LOGM;
+  constexpr int NW = Shape<LOGM>::WIDE ? 2 * m : 6 * m;               // wide: two transform buffers, no staged table
   uint2* tab = reinterpret_cast<uint2*>(sm + 4 * m);                 // staged twiddle table of the current (prime, direction)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + NW);
   uint32_t parity = 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  run_gates<LOGM, 3, false>(C, A, sm, tab, bar, parity, sm + 6 * m + 2);
+  run_gates<LOGM, 3, false>(C, A, sm, tab, bar, parity, sm + NW + 2);
 }
 
 template <int LOGM, bool HF>
@@ -1377,8 +1450,9 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
   using SH = Shape<LOGM>;
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR;
   uint32_t* zres = scratch + (size_t)blockIdx.x * SH::LM * m;
+  constexpr bool GTW = SH::WIDE;                          // m = 16384: two 64 KiB operands leave no room for a 128 KiB table
   uint2* tab = reinterpret_cast<uint2*>(sm + 2 * m);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 4 * m);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (GTW ? 2 * m : 4 * m));
   uint32_t parity = 0;
   if (threadIdx.x == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
@@ -1386,7 +1460,7 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
 #pragma unroll 1
     for (int i = 0; i < SH::LM; ++i) {
       const uint32_t p = C.p[i], p2 = 2 * p;
-      if (threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
+      if (!GTW && threadIdx.x == 0) stage_table(tab, tw_f + (size_t)i * m, m * 8, bar);
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_f + (size_t)i * m, wt);
       {
@@ -1415,17 +1489,17 @@ polymul_kernel(const __grid_constant__ DevConst C, const uint64_t* __restrict__ 
         }
       }
       __syncthreads();
-      mbar_wait(bar, parity); parity ^= 1;
-      ntt_passes<LOGM, 2, true>(sm, tab, p, C.zero);
-      if (threadIdx.x == 0) stage_table(tab, tw_i + (size_t)i * m, m * 8, bar);
+      if (!GTW) { mbar_wait(bar, parity); parity ^= 1; }
+      ntt_passes<LOGM, 2, true>(sm, GTW ? tw_f + (size_t)i * m : tab, p, C.zero);
+      if (!GTW && threadIdx.x == 0) stage_table(tab, tw_i + (size_t)i * m, m * 8, bar);
       for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
         uint32_t x = sm[swz(idx)], y = sm[m + swz(idx)];
         x = min(x, x - p2); x = min(x, x - p); y = min(y, y - p2); y = min(y, y - p);
         sm[swz(idx)] = redc((uint64_t)x * y, p, C.pinv_neg[i]);
       }
       __syncthreads();
-      mbar_wait(bar, parity); parity ^= 1;
-      ntt_passes<LOGM, 1, false>(sm, tab, p, C.zero);
+      if (!GTW) { mbar_wait(bar, parity); parity ^= 1; }
+      ntt_passes<LOGM, 1, false>(sm, GTW ? tw_i + (size_t)i * m : tab, p, C.zero);
       top_twiddles<REM>(tw_i + (size_t)i * m, wt);
       for (int idx = threadIdx.x; idx < STR; idx += blockDim.x) {
         uint32_t x[R];
@@ -1611,9 +1685,9 @@ __global__ void flatten_kernel(const __grid_constant__ DevConst C, const uint64_
     uint64_t dp0 = 0, dp1 = 0;
     const u96 vo = to_offset_form(C, from128(v));
 #define SGFHE_FLATTEN_CASE(LOGM_) case LOGM_: if (draws) decompose_off_rand<3 * LOGM_ - 1>(C, vo, draws[2 * idx], draws[2 * idx + 1], dp0, dp1); else decompose_off<3 * LOGM_ - 1>(C, vo, dp0, dp1); break;
-    switch (C.logm) { SGFHE_FLATTEN_CASE(9) SGFHE_FLATTEN_CASE(10) SGFHE_FLATTEN_CASE(11) SGFHE_FLATTEN_CASE(12) default: SGFHE_FLATTEN_CASE(13) }
+    switch (C.logm) { SGFHE_FLATTEN_CASE(9) SGFHE_FLATTEN_CASE(10) SGFHE_FLATTEN_CASE(11) SGFHE_FLATTEN_CASE(12) SGFHE_FLATTEN_CASE(14) default: SGFHE_FLATTEN_CASE(13) }
 #undef SGFHE_FLATTEN_CASE
-    d[0] = (int64_t)dp0 - ((int64_t)1 << 46); d[1] = (int64_t)dp1 - ((int64_t)1 << 46);
+    d[0] = (int64_t)dp0 - (int64_t)C.dig_bias; d[1] = (int64_t)dp1 - (int64_t)C.dig_bias;
   }
   for (int i = 0; i < 2; ++i) {
     const u128 r = d[i] >= 0 ? (u128)d[i] : C.Q - (u128)(-d[i]);
@@ -1817,7 +1891,8 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
   if (dc->sbits != 6 * hp.logm + 8) return -1;                             // compile-time shift of barrett96
   dc->barrett_inv = ldexp(1.0, dc->sbits - 16) / (double)hp.Q * (1.0 - ldexp(1.0, -40));
   dc->inv35 = nextafter(nextafter(1.0 / 35.0, 1.0), 1.0);
-  dc->s46 = ((uint64_t)1 << 46) - dc->s;
+  dc->dig_bias = (uint64_t)1 << (hp.logm >= 14 ? 48 : 46);                // |digit| <= 2B with the largest draws: 2^44.1 at n = 1024, 2^47.2 at n = 2048
+  dc->s46 = dc->dig_bias - dc->s;
   dc->xmax = (uint64_t)(hp.B / 2 * 3);
   {
     const u128 K = ((u128)L << 30) + L + 1, KQ = K * hp.Q;                 // < 2^34 Q < 2^124
@@ -1840,7 +1915,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
     if (5ull * ((1u << 30) - p) >= (1u << 30)) return -1;                  // centred_mod's reduction of the low word
     dc->mont[i] = dc->r32[i];
     dc->mont_sh[i] = (uint32_t)(((uint64_t)dc->mont[i] << 32) / p);
-    dc->dig_negc[i] = p - (uint32_t)(((uint64_t)1 << 46) % p) - 4u * p;      // wraps mod 2^32 on purpose
+    dc->dig_negc[i] = p - (uint32_t)(dc->dig_bias % p) - 4u * p;            // wraps mod 2^32 on purpose
     dc->hp_p[i] = (double)p; dc->hp_pinv[i] = 1.0 / (double)p; dc->hp_c[i] = 6755399441055744.0 + 2.0 * (double)p;
   }
   for (int basis = 0; basis < 2; ++basis) {
@@ -1903,13 +1978,14 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
 }
 
 
-// ---- LOGM dispatch: every kernel is compiled for m = 512 .. 8192 -------------------------------------------
+// ---- LOGM dispatch: every kernel is compiled for m = 512 .. 16384 (v4 kernels: 4096, 8192) -------------------------------------------
 #define SGFHE_DISPATCH(logm, STMT)                         \
   switch (logm) {                                          \
     case 9:  { constexpr int LOGM_ = 9;  STMT; } break;    \
     case 10: { constexpr int LOGM_ = 10; STMT; } break;    \
     case 11: { constexpr int LOGM_ = 11; STMT; } break;    \
     case 12: { constexpr int LOGM_ = 12; STMT; } break;    \
+    case 14: { constexpr int LOGM_ = 14; STMT; } break;    \
     default: { constexpr int LOGM_ = 13; STMT; } break;    \
   }
 
@@ -1921,7 +1997,7 @@ static int build_consts(const HostParams& hp, DevConst* dc, std::vector<uint2>* 
 
 static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   cudaError_t e = cudaSuccess;
-  c->use_v4 = c->hp.logm >= 12 && !getenv("SGFHE_FORCE_V3");
+  c->use_v4 = c->hp.logm >= 12 && c->hp.logm <= 13 && !getenv("SGFHE_FORCE_V3");
   c->head_f64 = !getenv("SGFHE_HEAD_INT");           // A/B knob: the all-integer head of round 1
   // experimental, off by default: two gates per SM.  Measured slower than v4 (231 k against 201 k cycles per gate-step): 296
   // gates in flight double the scratch working set to 246 MB, the L2 hit rate falls from 78 % to 48 % and the DRAM traffic per
@@ -1947,7 +2023,7 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
     c->threads = Shape<LOGM_>::T;
     if (!c->use_v4) c->boot_threads = c->threads;
     e = cudaFuncSetAttribute(bootstrap_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(key_transform_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(key_transform_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(c->smem_bytes, (size_t)c->hp.m * 12 + 16));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(polymul_kernel<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
     if (e == cudaSuccess && !c->use_v4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel<LOGM_>, c->threads, c->smem_bytes);
   });
@@ -1993,7 +2069,7 @@ static void launch_polymul(const sgfhe_ctx* c, int grid, cudaStream_t st, const 
     ++g_launches;
     return;
   }
-  SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * 16 + 16, st>>>(
+  SGFHE_DISPATCH(c->hp.logm, (polymul_kernel<LOGM_><<<grid, c->threads, (size_t)c->hp.m * (Shape<LOGM_>::WIDE ? 8 : 16) + 16, st>>>(
                                   c->dc, a, b, out, c->d_tw_f, c->d_tw_i, c->d_pm_scratch, batch, b_bcast)));
   ++g_launches;
 }
@@ -2029,7 +2105,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   const int rc = h_params(n, &hp);
   if (rc == -1) return fail(SGFHE_ERR_ARG, "n must be a power of two >= 64 (src/fhe.jl:45-46)");
   if (rc) return fail(SGFHE_ERR_MODULUS, "could not find a modulus / n is too large (src/utils.jl:26, src/fhe.jl:77)");
-  if (n > 1024) return fail(SGFHE_ERR_ARG, "this backend supports n <= 1024 (m = 8n <= 8192 on-chip NTT)");
+  if (n > 2048) return fail(SGFHE_ERR_ARG, "this backend supports n <= 2048 (Q < 2^96; src/fhe.jl:71-78 itself stops at 128 bits)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SGFHE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
   if (device < 0 || device >= ndev) return fail(SGFHE_ERR_ARG, "bad device ordinal");
@@ -2046,7 +2122,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
   }
   const int m = hp.m;
-  c->smem_bytes = (size_t)24 * m + 16 + 1024;                // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare)
+  c->smem_bytes = (size_t)(hp.logm >= 14 ? 8 : 24) * m + 16 + 1024;   // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare); m = 16384: two buffers, twiddles from global
   int occ = 0;
   CK(configure_kernels(c, &occ));
   {
@@ -2504,9 +2580,9 @@ extern "C" int sgfhe_bkey_generate(sgfhe_ctx* c, const uint8_t* sk, const uint64
   const int chunk = (int)std::max<size_t>(1, ((size_t)1 << 25) / (4 * m * 16) * 4);    // rows per pass: <= 128 MiB of a_rand
   // arena: sk | ext (m wide) | a | prod | e | coef
   const size_t crow = (size_t)(rows < chunk ? rows : chunk);
-  const size_t o_sk = 0, o_ext = 1024, o_a = o_ext + m * 16, o_prod = o_a + crow * 4 * m * 16, o_e = o_prod + crow * 4 * m * 16,
+  const size_t o_sk = 0, o_ext = 4096, o_a = o_ext + m * 16, o_prod = o_a + crow * 4 * m * 16, o_e = o_prod + crow * 4 * m * 16,
                o_coef = o_e + crow * 4 * m * 8, total = o_coef + crow * 8 * m * 16;
-  if (n > 1024) return fail(SGFHE_ERR_ARG, "n too large");
+  if (n > 4096) return fail(SGFHE_ERR_ARG, "n too large");          // the secret key occupies the first o_ext bytes of the arena
   rc = ensure_arena(c, total); if (rc) return rc;
   uint8_t* d = c->d_arena;
   std::vector<uint64_t> ext(m * 2, 0);

@@ -31,7 +31,7 @@ def test_library_is_sm100a_only(sg):
     assert archs == {"sm_100a"}, archs
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048])
 def test_params_derive_matches_oracle(sg, so, n):
     P, OP = sg.Params(n), so.Params(n)
     assert (P.n, P.t, P.m, P.r, P.q, P.Dr, P.Dq, P.Q, P.B, P.DQ_tilde) == \

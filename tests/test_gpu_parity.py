@@ -28,7 +28,7 @@ def _edge_polys(m, Q, so):
     return [z, one, top, full]
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048])
 def test_polymul_matches_oracle(so, sg, n):
     """DarkIntegers `Polynomial *` seam (called at src/fhe.jl:527-528): random and edge operands."""
     P, OP = sg.Params(n), so.Params(n)
@@ -44,7 +44,7 @@ def test_polymul_matches_oracle(so, sg, n):
     P.close()
 
 
-@pytest.mark.parametrize("n", [64, 512, 1024])
+@pytest.mark.parametrize("n", [64, 512, 1024, 2048])
 @pytest.mark.parametrize("use_rng", [False, True])
 def test_flatten_poly_matches_oracle(so, sg, n, use_rng):
     """flatten_poly (src/utils.jl:253-264), port of test/internals.test.jl:115-141 plus exact equality."""
@@ -81,7 +81,7 @@ def test_external_product_with_gadget_is_identity(so, sg, use_rng):
     P.close()
 
 
-@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("n", [64, 1024, 2048])
 @pytest.mark.parametrize("use_rng", [False, True])
 def test_external_product_matches_oracle(so, sg, n, use_rng):
     """external_product (src/fhe.jl:519-530) with a random full-size A"""
@@ -191,10 +191,10 @@ def test_public_api_roundtrip_p64(sg):
     P.close()
 
 
-@pytest.mark.parametrize("n", [128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [128, 256, 512, 1024, 2048])
 def test_bootstrap_trace_truncated_large(so, sg, n):
-    """every supported transform shape (m = 1024 ... 8192; 86-bit Q at n = 1024): first steps of the loop against the
-    oracle, both flatten modes"""
+    """every supported transform shape (m = 1024 ... 16384; 87-bit Q at n = 1024, 93-bit Q and six primes at n = 2048, the
+    largest n whose Q fits 96 bits): first steps of the loop against the oracle, both flatten modes"""
     P, OP = sg.Params(n), so.Params(n)
     steps = 3
     sk = so.make_secret(OP, 1)
@@ -568,7 +568,7 @@ def test_full_deterministic_gate_mid_sizes(so, sg, n):
     P.close()
 
 
-@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("n", [64, 1024, 2048])
 def test_worst_case_magnitudes(so, sg, n):
     """the approximate CRT (v from the top bits of each residue) and the FP64-assisted Barrett step at the edge of their
     bounds: every draw +-xmax, every key coefficient floor(Q/2) or floor(Q/2)+1 (centred +-Q/2), accumulator all Q-1 or

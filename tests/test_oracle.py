@@ -27,7 +27,7 @@ def test_params_match_survey_table(so):
     assert P.Q == 0x4c40000000000000154001 and P.Dr == 4096 and P.DQ == P.Q // 8
 
 
-@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048])
 def test_params_oracle_equals_model(so, n):
     P, M = so.Params(n), md.params(n)
     assert (P.n, P.r, P.q, P.Q, P.t, P.m, P.B, P.Dr, P.Dq, P.DQ) == (M.n, M.r, M.q, M.Q, M.t, M.m, M.B, M.Dr, M.Dq, M.DQ)
