@@ -54,8 +54,9 @@ typedef struct {
   uint64_t DQ_tilde[2]; /* fhe.jl:90 */
 } sgfhe_params;
 
-/* Params(n) + device context.  n: power of two, 64 <= n <= 1024 (the reference accepts larger n;
- * this backend's on-chip NTT is sized for m = 8n <= 8192).  device: CUDA ordinal.
+/* Params(n) + device context.  n: power of two, 64 <= n <= 2048 (the reference accepts every n whose Q fits
+ * 128 bits, src/fhe.jl:71-78; this backend carries Z_Q in three 32-bit limbs, Q < 2^96, which n = 2048 with its
+ * 93-bit Q is the last to satisfy).  device: CUDA ordinal.
  * Replaces: Params(n; ...) src/fhe.jl:43. */
 int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out);
 int sgfhe_ctx_destroy(sgfhe_ctx* ctx);

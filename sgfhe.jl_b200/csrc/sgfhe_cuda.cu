@@ -292,7 +292,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
 //   B  warps 0-7:  update + decomposition of polynomial 0 from shared memory
 //      warps 8-15: CRT sums of polynomial 1 -> global scratch S.sums (shared memory is still occupied)
 //   C  all warps:  update + decomposition of polynomial 1, sums read back from L2 (ld.cg)
-// MEASURED (round 2, gpurun_out/r2_ab12.txt): bit-exact, B takes 16.8k cycles against 21.0k for the two phases it replaces,
+// MEASURED (round 2, profiles/ab_r02_split_tail.txt): bit-exact, B takes 16.8k cycles against 21.0k for the two phases it replaces,
 // but C takes 27.3k against 10.4k -- 256 KiB of sums per step come back through the 42 B/clk/SM L2 port, and shared memory
 // cannot hold both polynomials' sums (2 x 128 KiB).  214.1k cycles/step against 198.4k: compiled only with -DSGFHE_TAIL_SPLIT.
 #ifdef SGFHE_TAIL_SPLIT
