@@ -620,15 +620,25 @@ __device__ void gate_final(const DevConst& C, const Scratch& S, uint64_t* out_an
 //   * HF (round 2, the default): the digits are stored as doubles and the digit reduction plus the first forward stage run
 //     on the FP64 pipe (head_stage1_f64), which the integer kernel left idle.
 // =========================================================================================================
-template <int LOGM>
+template <int LOGM, int TB_ = 1>
 struct Shape4 {
   static constexpr int M = 1 << LOGM;
   static constexpr int REM = LOGM % 3;            // 0 or 1 supported
   static constexpr int LR0 = 3 + REM, R0 = 1 << LR0;
-  static constexpr int T = M >> LR0;              // 512 threads: one top-stage block per thread and polynomial
+  static constexpr int TB = TB_;                  // top-stage blocks per thread and polynomial
+  static constexpr int STR0 = M >> LR0;           // stride of the top-stage blocks (512)
+  static constexpr int T = STR0 / TB;             // 512 threads (TB = 1), or 256 with two top-stage blocks per thread
   static constexpr int NB = (M / 8) / T;          // radix-8 blocks per thread and polynomial (1 or 2)
   static constexpr int L = Shape<LOGM>::L;
 };
+// GateTB<LOGM>::V = top-stage blocks per thread of the gate kernel.  V = 2 at m = 4096 gives 256-thread CTAs and TWO gates per SM
+// (96 KiB of shared memory and 32 k registers each) with the per-warp 512-point slices of m = 8192 (64-bit shared-memory
+// accesses, __syncwarp between the passes).  MEASURED (round 2, profiles/ab_r02_p512_two_ctas.txt): bit-exact; the strided
+// passes get 20 % cheaper per gate, the key MACs and the update 15 % dearer (two gates on different key rows share the L2
+// port), 107.0 k against 109.0 k cycles per gate-step, and with four instead of eight gates per CTA at 1 184 gates the batch
+// ends on a longer tail: 4 600 - 4 780 against 5 117 gates/s.  V = 1 everywhere.
+template <int LOGM> struct GateTB { static constexpr int V = 1; };
+template <int LOGM> struct GateShape4 : Shape4<LOGM, GateTB<LOGM>::V> {};
 
 
 // Between the top stages and the last inverse pass every element with index bits [9, LOGM) fixed is touched only by
@@ -643,14 +653,14 @@ __device__ __forceinline__ void group_bar64() {
 // exchange data inside a warp only: __syncwarp replaces the block-level barriers and the 16 warps drift freely.
 // The two blocks of a thread are ADJACENT: in the strided passes they share their twiddles and their elements are
 // neighbours in memory, so every access is 64 bits wide (half the LDS/STS instructions; swz keeps bit 0).
-template <int LOGM>
+template <int LOGM, int TB = 1>
 __device__ __forceinline__ int block_of(int tid, int q) {
-  using S4 = Shape4<LOGM>;
+  using S4 = Shape4<LOGM, TB>;
   return S4::NB == 2 ? (((tid >> 5) << 6) | ((tid & 31) << 1) | q) : tid + q * S4::T;
 }
-template <int LOGM>
+template <int LOGM, int TB = 1>
 __device__ __forceinline__ void slice_sync() {
-  if (Shape4<LOGM>::NB == 2) __syncwarp(); else group_bar64();
+  if (Shape4<LOGM, TB>::NB == 2) __syncwarp(); else group_bar64();
 }
 
 // twiddles of one radix-8 block from the staged forward table; the inverse passes take the MIRRORED forward entries
@@ -672,14 +682,14 @@ __device__ __forceinline__ void block_twiddles(const uint2* tab, int lvl, int g,
   }
 }
 
-template <int LOGM, int NPOLY, bool FWD, int B>
+template <int LOGM, int NPOLY, bool FWD, int B, int TB = 1>
 __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_t p, uint32_t z) {
-  using S4 = Shape4<LOGM>;
+  using S4 = Shape4<LOGM, TB>;
   constexpr int M = S4::M;
   const uint32_t p2 = 2 * p;
   if constexpr (S4::NB == 2 && B >= 1) {
     // blocks blk and blk + 1 (blk even): same twiddles, elements (e, e + 1) adjacent and 8-byte aligned
-    const int blk = block_of<LOGM>(threadIdx.x, 0);
+    const int blk = block_of<LOGM, TB>(threadIdx.x, 0);
     const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
     uint2 w[7];
     block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
@@ -712,7 +722,7 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   } else {
 #pragma unroll
   for (int q = 0; q < S4::NB; ++q) {
-    const int blk = block_of<LOGM>(threadIdx.x, q);
+    const int blk = block_of<LOGM, TB>(threadIdx.x, q);
     const int base = ((blk >> B) << (B + 3)) | (blk & ((1 << B) - 1));
     uint2 w[7];
     block_twiddles<FWD>(tab, M >> (B + 3), blk >> B, p, w);
@@ -738,21 +748,23 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
                              const uint2* __restrict__ tw_f, const DrawSrc draws_next, int u, bool ext,
                              bool decompose_next, uint2* tab, uint64_t* bar, uint32_t& parity,
                              unsigned long long* timing) {
-  using S4 = Shape4<LOGM>;
-  constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, L = S4::L;
+  constexpr int TB = GateTB<LOGM>::V;
+  using S4 = Shape4<LOGM, TB>;
+  constexpr int m = S4::M, R0 = S4::R0, LR0 = S4::LR0, T = S4::T, NB = S4::NB, L = S4::L, STR0 = S4::STR0, NI = 4 * TB;
   const int tid = threadIdx.x;
   long long tprev = timing ? clock64() : 0;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   // Digit words are prime independent.  Polynomials are processed in the order 2,3,0,1: buffers 2,3 are not read
   // by the previous prime's residue store, so that store overlaps the head of the next digit load.
-  const int st = swz(tid);                               // swz(tid + k T) = swz(tid) + k T  (T is a multiple of 256)
+  const int st = swz(tid);                               // swz(tid + k 256) = swz(tid) + k 256
+  // head / top-inverse work items: (polynomial, top-stage block tb of this thread): elements tid + tb T + k STR0, k < R0
   // HF: the digits are doubles and the first stage runs on the FP64 pipe (head_stage1_f64); otherwise biased words
   uint32_t dl[HF ? 1 : 2][HF ? 1 : R0], dh[HF ? 1 : 2][HF ? 1 : R0];
   double dd[HF ? 2 : 1][HF ? R0 : 1];
 #pragma unroll
   for (int k = 0; k < R0; ++k) {
-    if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * T];
-    else { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+    if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * STR0];
+    else { dl[0][k] = S.diglo[2 * m + tid + k * STR0]; dh[0][k] = S.dighi[2 * m + tid + k * STR0]; }
   }
 #pragma unroll 1
   for (int i = 0; i < L; ++i) {
@@ -762,44 +774,44 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
       const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
       const double fp = C.hp_p[i], fpinv = C.hp_pinv[i], fw = C.hp_w[i], fwp = C.hp_wp[i], fc = C.hp_c[i];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = (jj + 2) & 3;
-        if (jj + 1 < 4) {
-          const int jn = (jj + 3) & 3;
+      for (int it = 0; it < NI; ++it) {
+        const int j = (it / TB + 2) & 3, o = (it % TB) * T;
+        if (it + 1 < NI) {
+          const int jn = ((it + 1) / TB + 2) & 3, on = ((it + 1) % TB) * T;
 #pragma unroll
           for (int k = 0; k < R0; ++k) {
-            if constexpr (HF) dd[(jj + 1) & 1][k] = S.digd[jn * m + tid + k * T];
-            else { dl[(jj + 1) & 1][k] = S.diglo[jn * m + tid + k * T]; dh[(jj + 1) & 1][k] = S.dighi[jn * m + tid + k * T]; }
+            if constexpr (HF) dd[(it + 1) & 1][k] = S.digd[jn * m + tid + on + k * STR0];
+            else { dl[(it + 1) & 1][k] = S.diglo[jn * m + tid + on + k * STR0]; dh[(it + 1) & 1][k] = S.dighi[jn * m + tid + on + k * STR0]; }
           }
         }
         // no barrier before buffers 0,1 are overwritten: their last reader (the previous prime's residue store) read, in
-        // this same thread, exactly the addresses st + k T that are written here
+        // this same thread, exactly the addresses st + tb T + k STR0 that are written here
         uint32_t x[R0];
         if constexpr (HF) {
-          head_stage1_f64<R0>(dd[jj & 1], x, fp, fpinv, fw, fwp, fc);
+          head_stage1_f64<R0>(dd[it & 1], x, fp, fpinv, fw, fwp, fc);
           fwd_block_tail<LR0>(x, C.topf[i], p, p2, z);
         } else {
 #pragma unroll
-          for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[jj & 1][k], dh[jj & 1][k], mu, negc, p);
+          for (int k = 0; k < R0; ++k) x[k] = digit_mod(dl[it & 1][k], dh[it & 1][k], mu, negc, p);
           fwd_block<LR0>(x, C.topf[i], p, p2, z);
         }
 #pragma unroll
-        for (int k = 0; k < R0; ++k) sm[j * m + st + k * T] = x[k];
+        for (int k = 0; k < R0; ++k) sm[j * m + st + o + k * STR0] = x[k];
       }
     }
     __syncthreads();
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
     SGFHE_TICK(0);
-    pass8_v4<LOGM, 4, true, 6>(sm, tab, p, z);
-    slice_sync<LOGM>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
+    pass8_v4<LOGM, 4, true, 6, TB>(sm, tab, p, z);
+    slice_sync<LOGM, TB>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
     {                                                    // the first set is requested before the stride-8 pass
-      const int kb = key_pos<LOGM>(8 * block_of<LOGM>(tid, 0)), kh = key_pos<LOGM>(8 * block_of<LOGM>(tid, 0) + 4);
+      const int kb = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, 0)), kh = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, 0) + 4);
       kq[0][0] = __ldg(reinterpret_cast<const uint4*>(K + kb)); kq[0][1] = __ldg(reinterpret_cast<const uint4*>(K + kh));
       kq[0][2] = __ldg(reinterpret_cast<const uint4*>(K + m + kb)); kq[0][3] = __ldg(reinterpret_cast<const uint4*>(K + m + kh));
     }
-    pass8_v4<LOGM, 4, true, 3>(sm, tab, p, z);
+    pass8_v4<LOGM, 4, true, 3, TB>(sm, tab, p, z);
     __syncwarp();                                        // bits [0,6) stay inside groups of 8 consecutive threads
     SGFHE_TICK(1);
     // ---- fused: stride-1 forward pass + 8 key MACs per point + stride-1 inverse pass ------------------------
@@ -807,7 +819,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
       const uint32_t pinv = C.pinv_neg[i];
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        const int blk = block_of<LOGM>(tid, q), base = 8 * blk;
+        const int blk = block_of<LOGM, TB>(tid, q), base = 8 * blk;
         const int a0 = swz(base), a1 = a0 ^ 4;
         uint2 w[7];
         block_twiddles<true>(tab, m / 8, blk, p, w);
@@ -819,7 +831,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
           const int sidx = q * 4 + j;
           if (sidx + 1 < NB * 4) {                       // prefetch the next (block, poly) key words
             const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
-            const int kb = key_pos<LOGM>(8 * block_of<LOGM>(tid, nq)), kh = key_pos<LOGM>(8 * block_of<LOGM>(tid, nq) + 4);
+            const int kb = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, nq)), kh = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, nq) + 4);
             const uint32_t* r0 = K + (size_t)(2 * nj) * m;
             const uint32_t* r1 = K + (size_t)(2 * nj + 1) * m;
             kq[(sidx + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(r0 + kb)); kq[(sidx + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(r0 + kh));
@@ -861,14 +873,14 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     }
     __syncwarp();
     SGFHE_TICK(2);
-    pass8_v4<LOGM, 2, false, 3>(sm, tab, p, z);
-    slice_sync<LOGM>();
-    pass8_v4<LOGM, 2, false, 6>(sm, tab, p, z);
+    pass8_v4<LOGM, 2, false, 3, TB>(sm, tab, p, z);
+    slice_sync<LOGM, TB>();
+    pass8_v4<LOGM, 2, false, 6, TB>(sm, tab, p, z);
     if (i + 1 < L) {                                     // next prime's first digit words: requested before the barrier, so a
 #pragma unroll                                           // warp that arrives early waits with its loads already in flight
       for (int k = 0; k < R0; ++k) {
-        if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * T];
-        else { dl[0][k] = S.diglo[2 * m + tid + k * T]; dh[0][k] = S.dighi[2 * m + tid + k * T]; }
+        if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * STR0];
+        else { dl[0][k] = S.diglo[2 * m + tid + k * STR0]; dh[0][k] = S.dighi[2 * m + tid + k * STR0]; }
       }
     }
     __syncthreads();                                     // last reader of `tab` for this prime is done
@@ -883,16 +895,17 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     {
       const uint32_t sw = C.lastw[i], sws = C.lastw_sh[i];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int it = 0; it < 2 * TB; ++it) {
+        const int c = it / TB, o = (it % TB) * T;
         uint32_t x[R0];
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + k * T];
+        for (int k = 0; k < R0; ++k) x[k] = sm[c * m + st + o + k * STR0];
         inv_block_upper<LR0>(x, C.topi[i], p, p2, z);
 #pragma unroll
         for (int k = 0; k < R0 / 2; ++k) {
           const uint32_t s0 = x[k] + x[k + R0 / 2] + z, d0 = x[k] - x[k + R0 / 2] + p2;
-          S.zres[((size_t)i * 2 + c) * m + tid + k * T] = csub(min(s0, s0 - p2), p);
-          S.zres[((size_t)i * 2 + c) * m + tid + (k + R0 / 2) * T] = csub(shoup_mul(d0, sw, sws, p), p);
+          S.zres[((size_t)i * 2 + c) * m + tid + o + k * STR0] = csub(min(s0, s0 - p2), p);
+          S.zres[((size_t)i * 2 + c) * m + tid + o + (k + R0 / 2) * STR0] = csub(shoup_mul(d0, sw, sws, p), p);
         }
       }
     }
@@ -1358,7 +1371,7 @@ bootstrap_kernel(const __grid_constant__ DevConst C, const __grid_constant__ Gat
 }
 
 template <int LOGM, bool HF>
-__global__ void __launch_bounds__(Shape4<LOGM>::T, 1)
+__global__ void __launch_bounds__(GateShape4<LOGM>::T, GateTB<LOGM>::V)
 bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ GateArgs A) {
   extern __shared__ __align__(16) uint32_t sm[];
   constexpr int m = 1 << LOGM;
@@ -2005,11 +2018,12 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
   c->use_v5 = c->use_v4 && c->hp.logm == 13 && c->head_f64 && getenv("SGFHE_V5");
   if (c->use_v4) {
     SGFHE_DISPATCH_V4(c->hp.logm, {
-      c->boot_threads = Shape4<LOGM_>::T;
+      c->boot_threads = Shape4<LOGM_>::T;                  // standalone products
+      c->boot_threads_gate = GateShape4<LOGM_>::T;
       e = cudaFuncSetAttribute(polymul_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads, c->smem_bytes);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads_gate, c->smem_bytes);
     });
     if (e != cudaSuccess) return e;
     if (c->use_v5) {
@@ -2037,7 +2051,7 @@ static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, cons
   }
   if (c->use_v4) {
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads_gate); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[1]; int nattr = 0;
     if (c->persist_l2) {                               // accumulator + digits of the resident CTAs stay in L2 across steps
       attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
