@@ -264,13 +264,24 @@ def run_ours(args) -> None:
     douts = [torch.empty_like(d1) for _ in range(3)]
     stream = torch.cuda.current_stream()
 
+    seed = int(args.rng_seed)                            # 0: rng = nothing; else bootstrap(bkey, rng, ...) with device-side draws
+    gate0 = rank * batch                                 # disjoint Philox streams per rank
+
     def step_device():
-        _lib.check(L.sgfhe_bootstrap_batch_device(P.ctx, batch, d1.data_ptr(), d2.data_ptr(), None,
-                                                  *[o.data_ptr() for o in douts], stream.cuda_stream))
+        if seed:
+            _lib.check(L.sgfhe_bootstrap_batch_rng_device(P.ctx, batch, d1.data_ptr(), d2.data_ptr(), seed, gate0,
+                                                          *[o.data_ptr() for o in douts], stream.cuda_stream))
+        else:
+            _lib.check(L.sgfhe_bootstrap_batch_device(P.ctx, batch, d1.data_ptr(), d2.data_ptr(), None,
+                                                      *[o.data_ptr() for o in douts], stream.cuda_stream))
 
     def step_host():
-        _lib.check(L.sgfhe_bootstrap_batch(P.ctx, batch, h1.data_ptr(), h2.data_ptr(), None,
-                                           *[o.data_ptr() for o in houts]))
+        if seed:
+            _lib.check(L.sgfhe_bootstrap_batch_rng(P.ctx, batch, h1.data_ptr(), h2.data_ptr(), seed, gate0,
+                                                   *[o.data_ptr() for o in houts]))
+        else:
+            _lib.check(L.sgfhe_bootstrap_batch(P.ctx, batch, h1.data_ptr(), h2.data_ptr(), None,
+                                               *[o.data_ptr() for o in houts]))
 
     def barrier():
         torch.cuda.synchronize()
@@ -342,7 +353,7 @@ def run_ours(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32 (RNS residues of Z_Q, exact)", "data": "synthetic",
-            "config": {"workload": f"Params({n}) (m={P.m}, {qbits}-bit Q) batch of {batch} random gate bootstraps per GPU, rng=nothing" +
+            "config": {"workload": f"Params({n}) (m={P.m}, {qbits}-bit Q) batch of {batch} random gate bootstraps per GPU, " + ("rng=nothing" if not seed else f"rng=DeviceRng({seed}): randomised flatten, draws made on the device (Philox4x32-10)") +
                                    (f" (strong scaling: {args.batch} gates in total)" if args.scaling == "strong" else ""),
                        "n": n, "batch_per_gpu": batch, "parallelism": f"gates sharded over {world} GPU(s), key NCCL-broadcast once",
                        "l2": "working set (pre-transformed key %.2f GB + per-gate scratch) is larger than L2; no flush needed" % (key_bytes / 1e9)},
@@ -504,6 +515,7 @@ def main():
                     help="Params(n); under torchrun spell it --params-n (torchrun's own parser finds a bare --n ambiguous)")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--rng-seed", type=int, default=0, help="gates workload: 0 = rng=nothing (the default, BASELINE's config); S > 0 = the randomised flatten of bootstrap(bkey, rng, ...) with draws made on the device from seed S")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="budget of the cpu_baseline sample: 30 s fits whole gates at Params(1024)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = all host cores); a one-thread figure is reported next to it")

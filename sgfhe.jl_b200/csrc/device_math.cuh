@@ -391,8 +391,12 @@ __device__ __forceinline__ void decompose_off(const DevConst& C, u96 a, uint64_t
 template <int KB>
 __device__ __forceinline__ void decompose_off_rand(const DevConst& C, u96 a, int64_t x0, int64_t x1, uint64_t& dp0, uint64_t& dp1) {
   i128 X = (i128)x1 * (i128)C.B + (i128)x0;       // rand_a = a - x0 - x1 B   (src/utils.jl:222,232-233)
-  X %= (i128)C.Q;
-  if (X < 0) X += (i128)C.Q;
+  // X mod Q without a 128-bit division: |x| <= xmax = 3B/2 and Q > 0.997 B^2 (Q in [1220, 1225] r^4 n^2, B^2 = 1225 r^4 n^2),
+  // so |X| < 1.51 Q and two conditional corrections reach [0, Q)
+  const i128 Qs = (i128)C.Q;
+  if (X < 0) X += Qs;
+  if (X < 0) X += Qs;
+  if (X >= Qs) X -= Qs;
   a = from128(submodQ(to128(a), (u128)X, C.Q));
   decompose_off<KB>(C, a, dp0, dp1);
   dp0 += (uint64_t)x0;                            // + x                     (src/utils.jl:236-238)
