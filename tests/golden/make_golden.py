@@ -64,13 +64,19 @@ def gate_case(n, seed, pairs, steps, with_draws, check_model_steps):
     return out
 
 
+CASES = {
+    "golden_p64.npz": lambda: gate_case(64, 0, [(10, 20), (0, 63), (5, 6)], 64, True, 2),
+    "golden_p1024_trunc.npz": lambda: gate_case(1024, 1, [(3, 700)], 2, True, 1),
+    "golden_p512_trunc.npz": lambda: gate_case(512, 2, [(1, 2)], 2, False, 0),
+    "golden_p2048_trunc.npz": lambda: gate_case(2048, 3, [(5, 1500)], 2, True, 1),      # m = 16384, 93-bit Q, six primes on the GPU
+}
+
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(HERE, "golden_p64.npz"),
-                        **gate_case(64, 0, [(10, 20), (0, 63), (5, 6)], 64, True, 2))
-    np.savez_compressed(os.path.join(HERE, "golden_p1024_trunc.npz"),
-                        **gate_case(1024, 1, [(3, 700)], 2, True, 1))
-    np.savez_compressed(os.path.join(HERE, "golden_p512_trunc.npz"),
-                        **gate_case(512, 2, [(1, 2)], 2, False, 0))
+    # existing files are left alone (a zip archive is not byte-reproducible) unless --all is given
+    for name, make in CASES.items():
+        path = os.path.join(HERE, name)
+        if "--all" in sys.argv or not os.path.exists(path):
+            np.savez_compressed(path, **make())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

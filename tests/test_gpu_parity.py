@@ -384,6 +384,14 @@ def test_transformed_key_roundtrip(env64, sg, tmp_path):
     P3 = sg.Params(128)
     with pytest.raises(sg.SgfheError, match="other parameters"):
         sg.BootstrapKey.load_transformed(P3, path)
+    # a blob of an older format (before the CRT pre-scaling moved into the key words: version 2) must not load
+    blob = bytearray(open(path, "rb").read())
+    assert int.from_bytes(blob[4:8], "little") == 3
+    blob[4:8] = (2).to_bytes(4, "little")
+    old = str(tmp_path / "old.sgk")
+    open(old, "wb").write(bytes(blob))
+    with pytest.raises(sg.SgfheError, match="not a serialised sgfhe key"):
+        sg.BootstrapKey.load_transformed(P2, old)
     P2.close(); P3.close()
 
 
@@ -598,7 +606,7 @@ def test_worst_case_magnitudes(so, sg, n):
     P.close()
 
 
-@pytest.mark.parametrize("name", ["golden_p64.npz", "golden_p1024_trunc.npz", "golden_p512_trunc.npz"])
+@pytest.mark.parametrize("name", ["golden_p64.npz", "golden_p1024_trunc.npz", "golden_p512_trunc.npz", "golden_p2048_trunc.npz"])
 def test_gpu_reproduces_golden(so, sg, name):
     """the committed fixtures (tests/golden/, generator make_golden.py): the GPU path reproduces every stored output and
     the hash of every accumulator state"""

@@ -220,7 +220,7 @@ def test_batch_threads_equal_single(so, gate64):
     assert all(np.array_equal(o[4], x) for o, x in zip(o1, r))
 
 
-@pytest.mark.parametrize("name", ["golden_p64.npz", "golden_p1024_trunc.npz", "golden_p512_trunc.npz"])
+@pytest.mark.parametrize("name", ["golden_p64.npz", "golden_p1024_trunc.npz", "golden_p512_trunc.npz", "golden_p2048_trunc.npz"])
 def test_oracle_reproduces_golden(so, name):
     """committed fixtures (tests/golden/make_golden.py): inputs regenerate from the seed, outputs match"""
     g = np.load(os.path.join(GOLD, name))
