@@ -220,9 +220,6 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
     cp_async_commit();
   }
   // the accumulator was last touched a whole step ago: pull it from HBM into L2 while the CRT sums run
-#ifdef SGFHE_ACC_PREFETCH_EARLY
-  if (!OWN)                                                  // the v4 step has asked for it during its last prime
-#endif
   for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
   for (int c = 0; c < 2; ++c) {
@@ -805,12 +802,6 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     __syncthreads();
     mbar_wait(bar, parity); parity ^= 1;                 // forward table of this prime (staged one prime ago)
     SGFHE_TICK(0);
-#ifdef SGFHE_ACC_PREFETCH_EARLY
-    if (i == L - 1) {                                    // the accumulator is read again ~30 k cycles from here (tail of this step)
-      for (int line = tid; line < (2 * 3 * m * 4) / 128; line += T)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S.acc) + (size_t)line * 128));
-    }
-#endif
     pass8_v4<LOGM, 4, true, 6, TB>(sm, tab, p, z);
     slice_sync<LOGM, TB>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
