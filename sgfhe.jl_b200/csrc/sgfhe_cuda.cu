@@ -743,6 +743,24 @@ __device__ __forceinline__ void pass8_v4(uint32_t* sm, const uint2* tab, uint32_
   }
 }
 
+// Key tiles by TMA (-DSGFHE_KEY_TMA): the 2 x 1 KiB of key words a warp needs for one (radix-8 block, digit polynomial) --
+// rows 2j and 2j+1 of the pre-transformed key, 8 transform points per lane, contiguous for the whole warp thanks to key_pos --
+// arrive by two cp.async.bulk copies into a per-warp 2 KiB staging buffer, completing on a per-warp mbarrier; lane 0
+// requests the next pair as soon as the warp has moved the current one into registers.
+// MEASURED (round 2, profiles/ab_r02_key_tma.txt): bit-exact (78 GPU tests), but 227.8 k against 198.4 k cycles per step:
+// the fused phase goes from 47.8 k to 72.3 k.  Shared memory has room for ONE pair per warp (32 KiB next to 192 KiB of
+// transform buffers and twiddles), i.e. a lookahead of one (block, polynomial) of work, about 600 cycles, and a bulk copy
+// takes longer than that to land; the LDG.128 loads with a register double buffer (the default) have the same lookahead
+// and hide their latency.  Off by default.
+#ifdef SGFHE_KEY_TMA
+constexpr bool kKeyTma = true;
+#else
+constexpr bool kKeyTma = false;
+#endif
+constexpr int kKeyStageBytes = 16 * 2048 + 16 * 8;        // 16 warps x (2 rows x 1 KiB) + 16 mbarriers
+template <int LOGM>
+__device__ __forceinline__ uint8_t* key_stage_base(uint32_t* sm) { return reinterpret_cast<uint8_t*>(sm) + (size_t)24 * (1 << LOGM) + 128; }
+
 template <int LOGM, bool HF>
 __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, const uint32_t* __restrict__ keyrow,
                              const uint2* __restrict__ tw_f, const DrawSrc draws_next, int u, bool ext,
@@ -805,8 +823,23 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
     pass8_v4<LOGM, 4, true, 6, TB>(sm, tab, p, z);
     slice_sync<LOGM, TB>();                                  // bits [0,9) stay inside one slice (one warp, or 64 consecutive threads)
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
-    uint4 kq[2][4];                                      // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
-    {                                                    // the first set is requested before the stride-8 pass
+    uint4 kq[kKeyTma ? 1 : 2][4];                        // key words of (block, poly): rows 2j and 2j+1, 8 indices each;
+    // TMA path: this warp's staging buffer [2][256] words, its mbarrier, and the request of item sidx = 4 q + j by lane 0
+    const int warp = tid >> 5; [[maybe_unused]] const int lane = tid & 31;
+    uint32_t* kbuf = reinterpret_cast<uint32_t*>(key_stage_base<LOGM>(sm)) + warp * 512;
+    uint64_t* kbar = reinterpret_cast<uint64_t*>(key_stage_base<LOGM>(sm) + 16 * 2048) + warp;
+    auto key_chunk0 = [&](int q) { return key_pos<LOGM>(8 * block_of<LOGM, TB>(warp * 32, q)); };   // first word of the warp's 1 KiB run in a key row
+    auto key_request = [&](int sidx) {
+      const int q = sidx / 4, j = sidx % 4;
+      const uint32_t* r0 = K + (size_t)(2 * j) * m + key_chunk0(q);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's reads of the buffer (before the __syncwarp) are done
+      mbar_expect_tx(kbar, 2048);
+      bulk_g2s(kbuf, r0, 1024, kbar);
+      bulk_g2s(kbuf + 256, r0 + m, 1024, kbar);
+    };
+    if constexpr (kKeyTma) {
+      if (lane == 0) key_request(0);                     // the first pair is requested before the stride-8 pass
+    } else {                                             // the first set is requested before the stride-8 pass
       const int kb = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, 0)), kh = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, 0) + 4);
       kq[0][0] = __ldg(reinterpret_cast<const uint4*>(K + kb)); kq[0][1] = __ldg(reinterpret_cast<const uint4*>(K + kh));
       kq[0][2] = __ldg(reinterpret_cast<const uint4*>(K + m + kb)); kq[0][3] = __ldg(reinterpret_cast<const uint4*>(K + m + kh));
@@ -829,7 +862,15 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int sidx = q * 4 + j;
-          if (sidx + 1 < NB * 4) {                       // prefetch the next (block, poly) key words
+          if constexpr (kKeyTma) {
+            // items complete in order on the warp's mbarrier: phase parity = item parity (NB * 4 items per prime, an even number)
+            mbar_wait(kbar, sidx & 1);
+            const int o0 = key_pos<LOGM>(8 * blk) - key_chunk0(q), o1 = key_pos<LOGM>(8 * blk + 4) - key_chunk0(q);
+            kq[0][0] = *reinterpret_cast<const uint4*>(kbuf + o0); kq[0][1] = *reinterpret_cast<const uint4*>(kbuf + o1);
+            kq[0][2] = *reinterpret_cast<const uint4*>(kbuf + 256 + o0); kq[0][3] = *reinterpret_cast<const uint4*>(kbuf + 256 + o1);
+            __syncwarp();
+            if (sidx + 1 < NB * 4 && lane == 0) key_request(sidx + 1);
+          } else if (sidx + 1 < NB * 4) {                // prefetch the next (block, poly) key words
             const int nq = (sidx + 1) / 4, nj = (sidx + 1) % 4;
             const int kb = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, nq)), kh = key_pos<LOGM>(8 * block_of<LOGM, TB>(tid, nq) + 4);
             const uint32_t* r0 = K + (size_t)(2 * nj) * m;
@@ -844,7 +885,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
             x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
           }
           fwd_block<3>(x, w, p, p2, z);
-          const uint4* kk = kq[sidx & 1];
+          const uint4* kk = kq[kKeyTma ? 0 : (sidx & 1)];
           const uint32_t ka[8] = {kk[0].x, kk[0].y, kk[0].z, kk[0].w, kk[1].x, kk[1].y, kk[1].z, kk[1].w};
           const uint32_t kb[8] = {kk[2].x, kk[2].y, kk[2].z, kk[2].w, kk[3].x, kk[3].y, kk[3].z, kk[3].w};
 #pragma unroll
@@ -1379,7 +1420,9 @@ bootstrap_kernel_v4(const __grid_constant__ DevConst C, const __grid_constant__ 
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 6 * m);
   uint32_t parity = 0;
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_init(bar, 1);
+    if (kKeyTma) for (int w = 0; w < 16; ++w) mbar_init(reinterpret_cast<uint64_t*>(key_stage_base<LOGM>(sm) + 16 * 2048) + w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     stage_table(tab, A.tw_f, m * 8, bar);
   }
   __syncthreads();
@@ -1853,7 +1896,7 @@ struct sgfhe_ctx {
   bool use_v4 = false;
   bool head_f64 = true;                            // v4 gate kernel: digits as doubles, first forward stage on the FP64 pipe
   bool use_v5 = false;                             // m = 8192: two gates per SM (bootstrap_kernel_v5)
-  size_t smem_bytes = 0, scratch_stride = 0, zres_stride = 0;
+  size_t smem_bytes = 0, smem_gate_v4 = 0, scratch_stride = 0, zres_stride = 0;
   int persist_l2 = 0;                              // pin accumulator + digit scratch in L2 (access policy window)
   uint2* d_tw_f = nullptr; uint2* d_tw_i = nullptr;
   uint32_t* d_keyhat = nullptr; int key_rows = 0; size_t keyhat_capacity_rows = 0;
@@ -2021,9 +2064,9 @@ static cudaError_t configure_kernels(sgfhe_ctx* c, int* occ) {
       c->boot_threads = Shape4<LOGM_>::T;                  // standalone products
       c->boot_threads_gate = GateShape4<LOGM_>::T;
       e = cudaFuncSetAttribute(polymul_kernel_v4<LOGM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads_gate, c->smem_bytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_gate_v4);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(bootstrap_kernel_v4<LOGM_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_gate_v4);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, bootstrap_kernel_v4<LOGM_, true>, c->boot_threads_gate, c->smem_gate_v4);
     });
     if (e != cudaSuccess) return e;
     if (c->use_v5) {
@@ -2051,7 +2094,7 @@ static void launch_bootstrap(const sgfhe_ctx* c, int grid, cudaStream_t st, cons
   }
   if (c->use_v4) {
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads_gate); cfg.dynamicSmemBytes = c->smem_bytes; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(c->boot_threads_gate); cfg.dynamicSmemBytes = c->smem_gate_v4; cfg.stream = st;
     cudaLaunchAttribute attr[1]; int nattr = 0;
     if (c->persist_l2) {                               // accumulator + digits of the resident CTAs stay in L2 across steps
       attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
@@ -2137,6 +2180,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
   }
   const int m = hp.m;
   c->smem_bytes = (size_t)(hp.logm >= 14 ? 8 : 24) * m + 16 + 1024;   // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare); m = 16384: two buffers, twiddles from global
+  c->smem_gate_v4 = (size_t)24 * m + 128 + (kKeyTma ? kKeyStageBytes : 1024);          // + per-warp key staging buffers and their mbarriers
   int occ = 0;
   CK(configure_kernels(c, &occ));
   {
