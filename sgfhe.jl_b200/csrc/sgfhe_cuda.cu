@@ -198,7 +198,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   // sm4: [m] unreduced sums, 16 m bytes (the four transform buffers; global scratch in the v5 kernel); stg: staging area
-  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : 1;
+  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : (GSUM && NIT % 2 == 0 ? 2 : 1);
   uint32_t yq[D][L];
   u96 aq[D];
   if (OWN) {
@@ -534,6 +534,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
     top_twiddles<REM>(twf, wt);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
+#pragma unroll 2
       for (int e = tid; e < 2 * STR; e += T) {
         const int jj = e / STR, idx = e % STR, j = 2 * h + jj;
         uint32_t x[R];
@@ -546,6 +547,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
       __syncthreads();
       ntt_passes<LOGM, 2, true>(sm, twf, p, C.zero);
       const uint32_t* Kh = K + (size_t)(4 * h) * m;      // key rows 2 j + c of digit polynomials j = 2h, 2h + 1
+#pragma unroll 4
       for (int idx = tid; idx < m; idx += T) {
         const int si = swz(idx), kp = key_pos<LOGM>(idx);
         uint32_t d0 = sm[si], d1 = sm[m + si];
@@ -565,6 +567,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
     {
       uint2 wti[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(twi, wti);
+#pragma unroll 2
       for (int e = tid; e < 2 * STR; e += T) {
         const int c = e / STR, idx = e % STR;
         uint32_t x[R];
