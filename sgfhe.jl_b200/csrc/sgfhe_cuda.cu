@@ -523,6 +523,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
   constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T, L = SH::L;
   const int tid = threadIdx.x;
   long long tprev = timing ? clock64() : 0;
+#define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
 #pragma unroll 1
   for (int i = 0; i < L; ++i) {
     const uint32_t p = C.p[i], p2 = 2 * p, pinv = C.pinv_neg[i];
@@ -534,7 +535,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
     top_twiddles<REM>(twf, wt);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-#pragma unroll 2
+#pragma unroll 4
       for (int e = tid; e < 2 * STR; e += T) {
         const int jj = e / STR, idx = e % STR, j = 2 * h + jj;
         uint32_t x[R];
@@ -545,25 +546,44 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
         for (int k = 0; k < R; ++k) sm[jj * m + swz(idx + k * STR)] = x[k];
       }
       __syncthreads();
+      SGFHE_TICK(0);
       ntt_passes<LOGM, 2, true>(sm, twf, p, C.zero);
+      SGFHE_TICK(1);
       const uint32_t* Kh = K + (size_t)(4 * h) * m;      // key rows 2 j + c of digit polynomials j = 2h, 2h + 1
-#pragma unroll 4
-      for (int idx = tid; idx < m; idx += T) {
-        const int si = swz(idx), kp = key_pos<LOGM>(idx);
-        uint32_t d0 = sm[si], d1 = sm[m + si];
-        d0 = min(d0, d0 - p2); d0 = min(d0, d0 - p); d1 = min(d1, d1 - p2); d1 = min(d1, d1 - p);
-        const uint64_t sa = (uint64_t)d0 * __ldg(&Kh[kp]) + (uint64_t)d1 * __ldg(&Kh[2 * m + kp]);
-        const uint64_t sb = (uint64_t)d0 * __ldg(&Kh[m + kp]) + (uint64_t)d1 * __ldg(&Kh[3 * m + kp]);
-        uint32_t ra = redc(sa, p, pinv), rb = redc(sb, p, pinv);              // [0, 2p)
-        if (h == 0) { S.park[idx] = ra; S.park[m + idx] = rb; }              // read back by this same thread
-        else {
-          ra += S.park[idx]; rb += S.park[m + idx];
-          sm[si] = min(ra, ra - p2); sm[m + si] = min(rb, rb - p2);          // [0, 2p): input range of the inverse butterflies
+#pragma unroll 2
+      for (int i4 = tid; i4 < m / 4; i4 += T) {           // four consecutive points per thread: 128-bit accesses throughout
+        const int idx = 4 * i4, si = swz(idx), kp = key_pos<LOGM>(idx);      // swz and key_pos<14> keep aligned quads contiguous
+        const uint4 k00 = __ldg(reinterpret_cast<const uint4*>(Kh + kp)), k01 = __ldg(reinterpret_cast<const uint4*>(Kh + m + kp));
+        const uint4 k10 = __ldg(reinterpret_cast<const uint4*>(Kh + 2 * m + kp)), k11 = __ldg(reinterpret_cast<const uint4*>(Kh + 3 * m + kp));
+        const uint4 v0 = *reinterpret_cast<const uint4*>(sm + si), v1 = *reinterpret_cast<const uint4*>(sm + m + si);
+        uint4 pa = make_uint4(0, 0, 0, 0), pb = pa;
+        if (h == 1) { pa = *reinterpret_cast<const uint4*>(S.park + idx); pb = *reinterpret_cast<const uint4*>(S.park + m + idx); }
+        const uint32_t d0[4] = {v0.x, v0.y, v0.z, v0.w}, d1[4] = {v1.x, v1.y, v1.z, v1.w};
+        const uint32_t a0[4] = {k00.x, k00.y, k00.z, k00.w}, b0[4] = {k01.x, k01.y, k01.z, k01.w};
+        const uint32_t a1[4] = {k10.x, k10.y, k10.z, k10.w}, b1[4] = {k11.x, k11.y, k11.z, k11.w};
+        const uint32_t qa[4] = {pa.x, pa.y, pa.z, pa.w}, qb[4] = {pb.x, pb.y, pb.z, pb.w};
+        uint32_t ra[4], rb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t x0 = d0[e], x1 = d1[e];
+          x0 = min(x0, x0 - p2); x0 = min(x0, x0 - p); x1 = min(x1, x1 - p2); x1 = min(x1, x1 - p);
+          ra[e] = redc((uint64_t)x0 * a0[e] + (uint64_t)x1 * a1[e], p, pinv);          // [0, 2p)
+          rb[e] = redc((uint64_t)x0 * b0[e] + (uint64_t)x1 * b1[e], p, pinv);
+          if (h == 1) { ra[e] += qa[e]; rb[e] += qb[e]; ra[e] = min(ra[e], ra[e] - p2); rb[e] = min(rb[e], rb[e] - p2); }   // [0, 2p): input range of the inverse butterflies
+        }
+        if (h == 0) {                                     // read back by this same thread
+          *reinterpret_cast<uint4*>(S.park + idx) = make_uint4(ra[0], ra[1], ra[2], ra[3]);
+          *reinterpret_cast<uint4*>(S.park + m + idx) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
+        } else {
+          *reinterpret_cast<uint4*>(sm + si) = make_uint4(ra[0], ra[1], ra[2], ra[3]);
+          *reinterpret_cast<uint4*>(sm + m + si) = make_uint4(rb[0], rb[1], rb[2], rb[3]);
         }
       }
       __syncthreads();
+      SGFHE_TICK(2);
     }
     ntt_passes<LOGM, 2, false>(sm, twi, p, C.zero);
+    SGFHE_TICK(3);
     {
       uint2 wti[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(twi, wti);
@@ -579,7 +599,9 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
       }
     }
     __syncthreads();
+    SGFHE_TICK(4);
   }
+#undef SGFHE_TICK
   crt_update<LOGM, T, false, false, true>(C, S, S.sums, nullptr, draws_next, u, ext, decompose_next, timing, tprev);
 }
 
