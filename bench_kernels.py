@@ -52,11 +52,12 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / args.reps
 
-    for n in (64, 128, 256, 512, 1024):
+    for n in (64, 128, 256, 512, 1024, 2048):
         P = sg.Params(n)
         m, qbits = P.m, P.Q.bit_length()
         rng = np.random.default_rng(n)
-        shape = (args.batch, m, 2)
+        batch = max(64, (args.batch * 8192) // m)            # the same operand bytes (268 MB per operand array) at every ring degree
+        shape = (batch, m, 2)
         a = rng.integers(0, 1 << 62, size=shape, dtype=np.uint64)
         a[..., 1] = 0 if qbits <= 64 else a[..., 1] & np.uint64((1 << (qbits - 65)) - 1)     # canonical: below Q
         if qbits <= 64:
@@ -64,11 +65,11 @@ def main():
         da = torch.from_numpy(a.view(np.int64)).cuda()
         db = da.flip(0).contiguous()
         do = torch.empty_like(da)
-        ms = timed(lambda: _lib.check(L.sgfhe_polymul_device(P.ctx, args.batch, da.data_ptr(), db.data_ptr(), do.data_ptr(), stream.cuda_stream)))
+        ms = timed(lambda: _lib.check(L.sgfhe_polymul_device(P.ctx, batch, da.data_ptr(), db.data_ptr(), do.data_ptr(), stream.cuda_stream)))
         w = (qbits + 31) // 32
         modmuls = 3 * (m // 2) * (m.bit_length() - 1) + m                     # standalone product
-        rate = args.batch / (ms / 1e3)
-        print(json.dumps({"kernel": "polymul_kernel_v4" if m >= 4096 else "polymul_kernel", "workload": f"Params({n}): m={m}, {qbits}-bit Q, batch {args.batch}, both operands full size",
+        rate = batch / (ms / 1e3)
+        print(json.dumps({"kernel": "polymul_kernel_v4" if 4096 <= m <= 8192 else "polymul_kernel", "workload": f"Params({n}): m={m}, {qbits}-bit Q, batch {batch}, both operands full size",
                           "polymuls_per_s": rate, "ms": ms,
                           "roofline": {"bound": "int32-pipe", "achieved": rate * modmuls * (2 * w * w + w) / 1e9, "peak": imad / 1e9, "unit": "GIMAD/s",
                                        "frac": rate * modmuls * (2 * w * w + w) / imad},
