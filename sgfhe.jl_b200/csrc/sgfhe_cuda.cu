@@ -198,7 +198,7 @@ __device__ __forceinline__ void crt_update(const DevConst& C, const Scratch& S, 
   const int tid = threadIdx.x;
 #define SGFHE_TICK(slot) do { if (timing && threadIdx.x == 0) { const long long tn_ = clock64(); timing[slot] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
   // sm4: [m] unreduced sums, 16 m bytes (the four transform buffers; global scratch in the v5 kernel); stg: staging area
-  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : (GSUM && NIT % 2 == 0 ? 2 : 1);
+  constexpr int NIT = m / T, D = (T <= 512 && NIT % 4 == 0) ? 4 : (NIT % 2 == 0 ? 2 : 1);   // coefficients in flight per thread (64-register kernels: two)
   uint32_t yq[D][L];
   u96 aq[D];
   if (OWN) {
