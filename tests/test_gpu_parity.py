@@ -865,3 +865,24 @@ def test_two_gates_per_sm_variant_p1024(env1024, so, sg, monkeypatch):
         ra, ro, rx, rtr = so.bootstrap_internal(OP, key[:3], lwes[3], lwes[700], draws=draws, n_steps=3, trace=True, fast=True)
         assert np.array_equal(gtr, rtr) and np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
     P5.close()
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("switch", ["SGFHE_HEAD_INT", "SGFHE_FORCE_V3"])
+def test_selectable_kernel_variants_match_oracle(so, sg, monkeypatch, switch, n):
+    """the A/B variants that stay selectable in the library -- the all-integer head of the v4 step (SGFHE_HEAD_INT) and the
+    generic one-polynomial-per-thread-group step at m >= 4096 (SGFHE_FORCE_V3) -- reach the oracle's accumulators too"""
+    monkeypatch.setenv(switch, "1")
+    P, OP = sg.Params(n), so.Params(n)
+    steps = 3
+    sk = so.make_secret(OP, 5)
+    key = so.make_bkey(OP, sk, 5, rows=steps)
+    _, lwes = so.make_lwes(OP, sk, 5)
+    bkey = sg.BootstrapKey(params=P, key=key)
+    rng = np.random.default_rng(32)
+    xmax = OP.B // 2 * 3
+    for draws in (None, rng.integers(-xmax, xmax + 1, size=(steps, 2, OP.m, 2), dtype=np.int64)):
+        ga, go, gx, gtr = sg.bootstrap_trace(bkey, draws, lwes[7], lwes[9], n_steps=steps)
+        ra, ro, rx, rtr = so.bootstrap_internal(OP, key, lwes[7], lwes[9], draws=draws, n_steps=steps, trace=True, fast=True)
+        assert np.array_equal(gtr, rtr) and np.array_equal(ga, ra) and np.array_equal(go, ro) and np.array_equal(gx, rx)
+    P.close()
