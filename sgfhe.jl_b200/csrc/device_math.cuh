@@ -408,7 +408,7 @@ __device__ __forceinline__ u96 to_offset_form(const DevConst& C, u96 a) { return
 __device__ __forceinline__ u96 from_offset_form(const DevConst& C, u96 a) { return submod96(a, off96(C), Q96(C)); }
 
 // Signed digits (|d| < dig_bias) are stored biased, dp = d + dig_bias < 2^49, as two words: lo = dp mod 2^32, hi = dp >> 18.
-__device__ __forceinline__ void digit_words(uint64_t dp, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)dp; hi = (uint32_t)(dp >> 18); }
+__device__ __forceinline__ uint2 digit_words(uint64_t dp) { return make_uint2((uint32_t)dp, (uint32_t)(dp >> 18)); }
 // the NEGATED digit as a double (exact): bits 0x433 | dp are 2^52 + dp, and (2^52 + 2^46) - (2^52 + dp) = -d
 __device__ __forceinline__ double digit_f64(uint64_t dp) {
   return __dadd_rn(4573968371548160.0, -__hiloint2double((int)(0x43300000u | (uint32_t)(dp >> 32)), (int)(uint32_t)dp));

@@ -45,13 +45,12 @@ struct GateArgs {
 
 // acc: the accumulator (a, b) in OFFSET FORM x + offs mod Q (device_math.cuh), limb-major; dig: the biased digit words
 // (dp mod 2^32, dp >> 18) of its gadget decomposition; zres: CRT-ready residues of the two product polynomials.
-struct Scratch { uint32_t* acc; uint32_t* diglo; uint32_t* dighi; double* digd; uint32_t* zres; uint32_t* park; uint4* sums; };
+struct Scratch { uint32_t* acc; uint2* dig2; double* digd; uint32_t* zres; uint32_t* park; uint4* sums; };
 __device__ __forceinline__ Scratch carve(uint8_t* base, uint8_t* zbase, int m) {
   Scratch s;
   s.acc = reinterpret_cast<uint32_t*>(base);                         // [2][3][m]
-  s.diglo = reinterpret_cast<uint32_t*>(base + (size_t)24 * m);       // [4][m]
-  s.dighi = reinterpret_cast<uint32_t*>(base + (size_t)40 * m);       // [4][m]
-  s.digd = reinterpret_cast<double*>(base + (size_t)24 * m);          // [4][m] negated digits as doubles (FP64 head; same bytes as diglo + dighi)
+  s.dig2 = reinterpret_cast<uint2*>(base + (size_t)24 * m);          // [4][m] biased digit words (dp mod 2^32, dp >> 18) side by side: one 64-bit access per digit
+  s.digd = reinterpret_cast<double*>(base + (size_t)24 * m);          // [4][m] negated digits as doubles (FP64 head; same bytes as dig2)
   s.zres = reinterpret_cast<uint32_t*>(zbase);                        // [L][2][m]
   s.park = reinterpret_cast<uint32_t*>(zbase + (size_t)64 * m);       // v5: [4][m/2] forward halves + [2][m/2] inverse halves (zres uses at most 8 * 8 m bytes)
   s.sums = reinterpret_cast<uint4*>(zbase + (size_t)76 * m);          // v5: [m] unreduced CRT sums
@@ -128,8 +127,8 @@ __device__ __forceinline__ void decompose_poly(const DevConst& C, const Scratch&
     else decompose_off<KB>(C, v, dp0, dp1);
     if (F64) { S.digd[(2 * c) * m + idx] = digit_f64(dp0); S.digd[(2 * c + 1) * m + idx] = digit_f64(dp1); }
     else {
-      digit_words(dp0, S.diglo[(2 * c) * m + idx], S.dighi[(2 * c) * m + idx]);
-      digit_words(dp1, S.diglo[(2 * c + 1) * m + idx], S.dighi[(2 * c + 1) * m + idx]);
+      S.dig2[(2 * c) * m + idx] = digit_words(dp0);
+      S.dig2[(2 * c + 1) * m + idx] = digit_words(dp1);
     }
   }
 }
@@ -178,8 +177,8 @@ __device__ __forceinline__ void update_poly(const DevConst& C, const Scratch& S,
         else decompose_off<KB>(C, res, dp0, dp1);
         if (F64) { S.digd[(2 * c) * m + j] = digit_f64(dp0); S.digd[(2 * c + 1) * m + j] = digit_f64(dp1); }
         else {
-          digit_words(dp0, S.diglo[(2 * c) * m + j], S.dighi[(2 * c) * m + j]);
-          digit_words(dp1, S.diglo[(2 * c + 1) * m + j], S.dighi[(2 * c + 1) * m + j]);
+          S.dig2[(2 * c) * m + j] = digit_words(dp0);
+          S.dig2[(2 * c + 1) * m + j] = digit_words(dp1);
         }
       }
     }
@@ -424,7 +423,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
       for (int q = 0; q < U; ++q) {
         const int e = tid + q * T, j = e / STR, idx = e % STR;
 #pragma unroll
-        for (int k = 0; k < R; ++k) { lo[0][q][k] = S.diglo[j * m + idx + k * STR]; hi[0][q][k] = S.dighi[j * m + idx + k * STR]; }
+        for (int k = 0; k < R; ++k) { const uint2 v = S.dig2[j * m + idx + k * STR]; lo[0][q][k] = v.x; hi[0][q][k] = v.y; }
       }
 #pragma unroll
       for (int b = 0; b < NBATCH; ++b) {
@@ -433,7 +432,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
           for (int q = 0; q < U; ++q) {
             const int e = tid + ((b + 1) * U + q) * T, j = e / STR, idx = e % STR;
 #pragma unroll
-            for (int k = 0; k < R; ++k) { lo[(b + 1) & 1][q][k] = S.diglo[j * m + idx + k * STR]; hi[(b + 1) & 1][q][k] = S.dighi[j * m + idx + k * STR]; }
+            for (int k = 0; k < R; ++k) { const uint2 v = S.dig2[j * m + idx + k * STR]; lo[(b + 1) & 1][q][k] = v.x; hi[(b + 1) & 1][q][k] = v.y; }
           }
         }
 #pragma unroll
@@ -540,7 +539,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
         const int jj = e / STR, idx = e % STR, j = 2 * h + jj;
         uint32_t x[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = digit_mod(S.diglo[j * m + idx + k * STR], S.dighi[j * m + idx + k * STR], mu, negc, p);
+        for (int k = 0; k < R; ++k) { const uint2 v = S.dig2[j * m + idx + k * STR]; x[k] = digit_mod(v.x, v.y, mu, negc, p); }
         fwd_block<REM>(x, wt, p, p2, C.zero);
 #pragma unroll
         for (int k = 0; k < R; ++k) sm[jj * m + swz(idx + k * STR)] = x[k];
@@ -807,7 +806,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll
   for (int k = 0; k < R0; ++k) {
     if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * STR0];
-    else { dl[0][k] = S.diglo[2 * m + tid + k * STR0]; dh[0][k] = S.dighi[2 * m + tid + k * STR0]; }
+    else { const uint2 v = S.dig2[2 * m + tid + k * STR0]; dl[0][k] = v.x; dh[0][k] = v.y; }
   }
 #pragma unroll 1
   for (int i = 0; i < L; ++i) {
@@ -824,7 +823,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll
           for (int k = 0; k < R0; ++k) {
             if constexpr (HF) dd[(it + 1) & 1][k] = S.digd[jn * m + tid + on + k * STR0];
-            else { dl[(it + 1) & 1][k] = S.diglo[jn * m + tid + on + k * STR0]; dh[(it + 1) & 1][k] = S.dighi[jn * m + tid + on + k * STR0]; }
+            else { const uint2 v = S.dig2[jn * m + tid + on + k * STR0]; dl[(it + 1) & 1][k] = v.x; dh[(it + 1) & 1][k] = v.y; }
           }
         }
         // no barrier before buffers 0,1 are overwritten: their last reader (the previous prime's residue store) read, in
@@ -946,7 +945,7 @@ __device__ void gate_step_v4(const DevConst& C, const Scratch& S, uint32_t* sm, 
 #pragma unroll                                           // warp that arrives early waits with its loads already in flight
       for (int k = 0; k < R0; ++k) {
         if constexpr (HF) dd[0][k] = S.digd[2 * m + tid + k * STR0];
-        else { dl[0][k] = S.diglo[2 * m + tid + k * STR0]; dh[0][k] = S.dighi[2 * m + tid + k * STR0]; }
+        else { const uint2 v = S.dig2[2 * m + tid + k * STR0]; dl[0][k] = v.x; dh[0][k] = v.y; }
       }
     }
     __syncthreads();                                     // last reader of `tab` for this prime is done
