@@ -456,29 +456,31 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     const uint32_t* K = keyrow + (size_t)i * 8 * m;      // [4][2][m] for this prime   (src/fhe.jl:527-528)
     const uint32_t pinv = C.pinv_neg[i];
     {
-      // software pipeline: the key words of the next two indices are in flight while one index is multiplied
-      constexpr int NIT = m / T;
-      uint32_t kq[3][8];
+      // two neighbouring points per thread and iteration: 64-bit key loads and shared-memory accesses (swz and key_pos keep an
+      // aligned pair adjacent); the key words of the next pair are in flight while one pair is multiplied
+      constexpr int NPI = m / (2 * T);
+      uint2 kq[2][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { kq[0][q] = __ldg(&K[q * m + key_pos<LOGM>(tid)]); if (NIT > 1) kq[1][q] = __ldg(&K[q * m + key_pos<LOGM>(tid + T)]); }
+      for (int q = 0; q < 8; ++q) kq[0][q] = __ldg(reinterpret_cast<const uint2*>(&K[q * m + key_pos<LOGM>(2 * tid)]));
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int idx = tid + it * T;
-        if (it + 2 < NIT) {
+      for (int it = 0; it < NPI; ++it) {
+        const int idx = 2 * (tid + it * T);
+        if (it + 1 < NPI) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) kq[(it + 2) % 3][q] = __ldg(&K[q * m + key_pos<LOGM>(idx + 2 * T)]);
+          for (int q = 0; q < 8; ++q) kq[(it + 1) & 1][q] = __ldg(reinterpret_cast<const uint2*>(&K[q * m + key_pos<LOGM>(idx + 2 * T)]));
         }
-        uint64_t sa = 0, sb = 0;
+        uint64_t sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
         const int si = swz(idx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t d = sm[j * m + si];
-          d = min(d, d - p2); d = min(d, d - p);
-          sa += (uint64_t)d * kq[it % 3][2 * j];
-          sb += (uint64_t)d * kq[it % 3][2 * j + 1];
+          uint2 d = *reinterpret_cast<const uint2*>(sm + j * m + si);
+          d.x = min(d.x, d.x - p2); d.x = min(d.x, d.x - p); d.y = min(d.y, d.y - p2); d.y = min(d.y, d.y - p);
+          const uint2 ka = kq[it & 1][2 * j], kb = kq[it & 1][2 * j + 1];
+          sa0 += (uint64_t)d.x * ka.x; sa1 += (uint64_t)d.y * ka.y;
+          sb0 += (uint64_t)d.x * kb.x; sb1 += (uint64_t)d.y * kb.y;
         }
-        sm[si] = redc(sa, p, pinv);
-        sm[m + si] = redc(sb, p, pinv);
+        *reinterpret_cast<uint2*>(sm + si) = make_uint2(redc(sa0, p, pinv), redc(sa1, p, pinv));
+        *reinterpret_cast<uint2*>(sm + m + si) = make_uint2(redc(sb0, p, pinv), redc(sb1, p, pinv));
       }
     }
     __syncthreads();
