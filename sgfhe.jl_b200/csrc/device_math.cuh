@@ -298,25 +298,27 @@ __device__ __forceinline__ void ntt_pass8(uint32_t* sm, const uint2* tw, uint32_
 
 template <int LOGM, int NPOLY, bool FWD, int K>
 struct PassLoop {
-  static __device__ __forceinline__ void run(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
+  static __device__ __forceinline__ void run(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z, const uint2* tw_low = nullptr) {
     constexpr int NP = Shape<LOGM>::NPASS;
     constexpr int B = FWD ? 3 * (NP - 1 - K) : 3 * K;
-    ntt_pass8<LOGM, NPOLY, FWD, B>(sm, tw, p, z);
+    // tw_low: a copy of table entries [0, M/8) (all the strided passes read: the pass with active bits [B, B+3) uses entries
+    // below M >> B), e.g. in shared memory while the full table stays in global memory (wide kernels)
+    ntt_pass8<LOGM, NPOLY, FWD, B>(sm, (B >= 3 && tw_low) ? tw_low : tw, p, z);
     // bits [0,6) of the index stay inside one group of 8 consecutive threads (one warp): the stride-8 and
     // stride-1 passes exchange data only within that group, so a warp-level barrier separates them.
     if ((FWD && B == 3) || (!FWD && B == 0 && NP > 1)) __syncwarp(); else __syncthreads();
-    PassLoop<LOGM, NPOLY, FWD, K + 1>::run(sm, tw, p, z);
+    PassLoop<LOGM, NPOLY, FWD, K + 1>::run(sm, tw, p, z, tw_low);
   }
 };
 template <int LOGM, int NPOLY, bool FWD>
 struct PassLoop<LOGM, NPOLY, FWD, Shape<LOGM>::NPASS> {
-  static __device__ __forceinline__ void run(uint32_t*, const uint2*, uint32_t, uint32_t) {}
+  static __device__ __forceinline__ void run(uint32_t*, const uint2*, uint32_t, uint32_t, const uint2* = nullptr) {}
 };
 // the NPASS radix-8 passes over bits [0, 3 NPASS); each pass ends with __syncthreads().
 // Forward: high bits first (after the fused REM top stages); inverse: low bits first.
 template <int LOGM, int NPOLY, bool FWD>
-__device__ __forceinline__ void ntt_passes(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z) {
-  PassLoop<LOGM, NPOLY, FWD, 0>::run(sm, tw, p, z);
+__device__ __forceinline__ void ntt_passes(uint32_t* sm, const uint2* tw, uint32_t p, uint32_t z, const uint2* tw_low = nullptr) {
+  PassLoop<LOGM, NPOLY, FWD, 0>::run(sm, tw, p, z, tw_low);
 }
 
 // uniform twiddles of the fused top stages: tw[1 .. 2^REM - 1]

@@ -534,6 +534,14 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
     const uint32_t mu = C.dig_mu[i], negc = C.dig_negc[i];
     uint2 wt[R > 1 ? R - 1 : 1];
     top_twiddles<REM>(twf, wt);
+    // entries [0, m/8) of both tables (all that the strided passes read: 2 x 16 KiB) go to shared memory behind the two transform
+    // buffers; only the stride-1 passes read their twiddles from global memory.  Visible after the barrier that ends the digit load.
+    uint2* twl_f = reinterpret_cast<uint2*>(sm + 2 * m + 64);
+    uint2* twl_i = twl_f + m / 8;
+    for (int e = tid; e < m / 16; e += T) {
+      reinterpret_cast<uint4*>(twl_f)[e] = __ldg(reinterpret_cast<const uint4*>(twf) + e);
+      reinterpret_cast<uint4*>(twl_i)[e] = __ldg(reinterpret_cast<const uint4*>(twi) + e);
+    }
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
 #pragma unroll 4
@@ -548,7 +556,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
       }
       __syncthreads();
       SGFHE_TICK(0);
-      ntt_passes<LOGM, 2, true>(sm, twf, p, C.zero);
+      ntt_passes<LOGM, 2, true>(sm, twf, p, C.zero, twl_f);
       SGFHE_TICK(1);
       const uint32_t* Kh = K + (size_t)(4 * h) * m;      // key rows 2 j + c of digit polynomials j = 2h, 2h + 1
 #pragma unroll 2
@@ -583,7 +591,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
       __syncthreads();
       SGFHE_TICK(2);
     }
-    ntt_passes<LOGM, 2, false>(sm, twi, p, C.zero);
+    ntt_passes<LOGM, 2, false>(sm, twi, p, C.zero, twl_i);
     SGFHE_TICK(3);
     {
       uint2 wti[R > 1 ? R - 1 : 1];
@@ -2205,7 +2213,7 @@ extern "C" int sgfhe_ctx_create(int32_t n, int32_t device, sgfhe_ctx** out) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize);
   }
   const int m = hp.m;
-  c->smem_bytes = (size_t)(hp.logm >= 14 ? 8 : 24) * m + 16 + 1024;   // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare); m = 16384: two buffers, twiddles from global
+  c->smem_bytes = (size_t)(hp.logm >= 14 ? 10 : 24) * m + 16 + 1024;   // 4 NTT buffers + staged twiddle table + mbarrier, work-counter word (+ spare); m = 16384: two buffers, twiddles from global
   c->smem_gate_v4 = (size_t)24 * m + 128 + (kKeyTma ? kKeyStageBytes : 1024);          // + per-warp key staging buffers and their mbarriers
   int occ = 0;
   CK(configure_kernels(c, &occ));
