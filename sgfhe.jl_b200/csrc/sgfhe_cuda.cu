@@ -395,6 +395,38 @@ __device__ __forceinline__ void crt_update_split(const DevConst& C, const Scratc
 }
 #endif
 
+// Last REM inverse stages of the two result polynomials (shared memory, swizzled) and store of the canonical residues, V
+// neighbouring columns per thread so that the shared-memory reads and the global stores are 16 / 8 bytes wide when the CTA has
+// fewer threads than columns (swz keeps an aligned group of four adjacent).  The CRT pre-scaling rides in the key words.
+template <int LOGM>
+__device__ __forceinline__ void store_residues(uint32_t* __restrict__ zres, const uint32_t* sm, const uint2* wt, uint32_t p, uint32_t z) {
+  using SH = Shape<LOGM>;
+  constexpr int m = SH::M, REM = SH::REM, R = 1 << REM, STR = SH::STR, T = SH::T;
+  constexpr int V = 2 * STR / T >= 4 ? 4 : (2 * STR / T >= 2 ? 2 : 1);
+  const uint32_t p2 = 2 * p;
+#pragma unroll 2
+  for (int e = (int)threadIdx.x * V; e < 2 * STR; e += T * V) {
+    const int c = e / STR, idx = e % STR;
+    uint32_t x[V][R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const uint32_t* src = sm + c * m + swz(idx + k * STR);
+      if constexpr (V == 4) { const uint4 v = *reinterpret_cast<const uint4*>(src); x[0][k] = v.x; x[1][k] = v.y; x[2][k] = v.z; x[3][k] = v.w; }
+      else if constexpr (V == 2) { const uint2 v = *reinterpret_cast<const uint2*>(src); x[0][k] = v.x; x[1][k] = v.y; }
+      else x[0][k] = *src;
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) inv_block<REM>(x[v], wt, p, p2, z);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      uint32_t* dst = zres + (size_t)c * m + idx + k * STR;
+      if constexpr (V == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(csub(x[0][k], p), csub(x[1][k], p), csub(x[2][k], p), csub(x[3][k], p));
+      else if constexpr (V == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(csub(x[0][k], p), csub(x[1][k], p));
+      else *dst = csub(x[0][k], p);
+    }
+  }
+}
+
 // One accumulation step (body of src/fhe.jl:579-582) on digits already in S.dig; leaves the new accumulator in
 // S.acc and its decomposition (with `draws_next`, the following step's draws) in S.dig.  u = rotation in [0, 2m).
 template <int LOGM>
@@ -491,17 +523,7 @@ __device__ void gate_step(const DevConst& C, const Scratch& S, uint32_t* sm, con
     {
       uint2 wt[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(tw_i + (size_t)i * m, wt);
-#pragma unroll 4
-      for (int e = tid; e < 2 * STR; e += T) {
-        const int c = e / STR, idx = e % STR;
-        uint32_t x[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = sm[c * m + swz(idx + k * STR)];
-        inv_block<REM>(x, wt, p, p2, C.zero);
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(x[k], p);   // the CRT pre-scaling rides in the key words
-      }
+      store_residues<LOGM>(S.zres + (size_t)i * 2 * m, sm, wt, p, C.zero);
     }
     __syncthreads();
     SGFHE_TICK(4);
@@ -596,16 +618,7 @@ __device__ void gate_step_wide(const DevConst& C, const Scratch& S, uint32_t* sm
     {
       uint2 wti[R > 1 ? R - 1 : 1];
       top_twiddles<REM>(twi, wti);
-#pragma unroll 2
-      for (int e = tid; e < 2 * STR; e += T) {
-        const int c = e / STR, idx = e % STR;
-        uint32_t x[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = sm[c * m + swz(idx + k * STR)];
-        inv_block<REM>(x, wti, p, p2, C.zero);
-#pragma unroll
-        for (int k = 0; k < R; ++k) S.zres[((size_t)i * 2 + c) * m + idx + k * STR] = csub(x[k], p);   // the CRT pre-scaling rides in the key words
-      }
+      store_residues<LOGM>(S.zres + (size_t)i * 2 * m, sm, wti, p, C.zero);
     }
     __syncthreads();
     SGFHE_TICK(4);
